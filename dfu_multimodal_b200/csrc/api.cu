@@ -1,0 +1,47 @@
+// Library-level entry points: error text, device checks.
+#include "common.cuh"
+#include "../../include/dfu_b200.h"
+#include <stdarg.h>
+#include <stdio.h>
+
+static thread_local char g_err[512] = "";
+
+void dfu_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int dfu_num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern "C" const char* dfu_last_error(void) { return g_err; }
+extern "C" int dfu_version(void) { return 100; }
+extern "C" int dfu_sm_count(void) { return dfu_num_sms(); }
+
+extern "C" int dfu_device_ok(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        dfu_set_error("no CUDA device: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return DFU_ERR_CUDA;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        dfu_set_error("device %d has compute capability %d.x; libdfu_b200 is sm_100a only", dev, major);
+        return DFU_ERR_UNSUPPORTED;
+    }
+    return DFU_OK;
+}

@@ -1,0 +1,460 @@
+// BatchNorm2d (training + eval, forward + backward) over NHWC bf16 [M, C] matrices, LayerNorm over rows,
+// and row softmax.  All are HBM-bound: 128-bit accesses along C / D, fp32 statistics, warp-shuffle reductions.
+#include "common.cuh"
+#include "../../include/dfu_b200.h"
+
+namespace {
+
+inline int grid_cap(long long blocks, int per_sm) {
+    long long cap = (long long)dfu_num_sms() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------ BatchNorm
+// Thread layout: 256 threads = (256/cvec) row lanes x cvec channel vectors (8 channels each).
+// MODE 0: sums of y and y^2.  MODE 1 (backward): sums of dpre and dpre*xhat.
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z,
+                                                        const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+                                                        float* __restrict__ sums, long long M, int C, int relu) {
+    __shared__ float red[2][256][9];   // padded against bank conflicts
+    const int cvec = C >> 3;
+    const int rows_per_iter = 256 / cvec;
+    const int cv = threadIdx.x % cvec;
+    const int rl = threadIdx.x / cvec;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    float mean[8], invstd[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            mean[i] = mean_invstd[cv * 8 + i];
+            invstd[i] = mean_invstd[C + cv * 8 + i];
+        }
+    }
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
+        const long long off = r * C + cv * 8;
+        float f[8];
+        if (MODE == 0) {
+            unpack8(ld8(a + off), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
+        } else {
+            float zz[8], yy[8];
+            unpack8(ld8(a + off), f);     // dz
+            unpack8(ld8(y + off), yy);
+            if (relu) {
+                unpack8(ld8(z + off), zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) f[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xh = (yy[i] - mean[i]) * invstd[i];
+                s1[i] += f[i];
+                s2[i] += f[i] * xh;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s1[i]; red[1][threadIdx.x][i] = s2[i]; }
+    __syncthreads();
+    // threads 0..cvec*8-1 each finish one channel (loop if C > 256)
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int v = c >> 3, i = c & 7;
+        float t1 = 0.f, t2 = 0.f;
+        for (int k = 0; k < rows_per_iter; ++k) { t1 += red[0][k * cvec + v][i]; t2 += red[1][k * cvec + v][i]; }
+        atomicAdd(sums + c, t1);
+        atomicAdd(sums + C + c, t2);
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean_invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, long long M, int C, float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    const float inv_m = 1.f / (float)M;
+    const float mean = sums[c] * inv_m;
+    float var = sums[C + c] * inv_m - mean * mean;
+    var = fmaxf(var, 0.f);
+    mean_invstd[c] = mean;
+    mean_invstd[C + c] = rsqrtf(var + eps);
+    if (running_mean) {
+        const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv,
+                                     float* __restrict__ mean_invstd, int C, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean_invstd[c] = rm[c];
+    mean_invstd[C + c] = rsqrtf(rv[c] + eps);
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const bf16* __restrict__ res, bf16* __restrict__ z, long long M,
+                                                       int C, int relu) {
+    const int cvec = C >> 3;
+    const int rows_per_iter = 256 / cvec;
+    const int cv = threadIdx.x % cvec;
+    const int rl = threadIdx.x / cvec;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        sc[i] = gamma[c] * mean_invstd[C + c];
+        sh[i] = beta[c] - mean_invstd[c] * sc[i];
+    }
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
+        const long long off = r * C + cv * 8;
+        float f[8];
+        unpack8(ld8(y + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
+        if (res) {
+            float rr[8];
+            unpack8(ld8(res + off), rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += rr[i];
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        st8(z + off, pack8(f));
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z,
+                                                           const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                           bf16* __restrict__ dy, bf16* __restrict__ dres,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           long long M, int C, int relu, int train) {
+    const int cvec = C >> 3;
+    const int rows_per_iter = 256 / cvec;
+    const int cv = threadIdx.x % cvec;
+    const int rl = threadIdx.x / cvec;
+    float mean[8], invstd[8], g[8], k1[8], k2[8];
+    const float inv_m = 1.f / (float)M;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        mean[i] = mean_invstd[c];
+        invstd[i] = mean_invstd[C + c];
+        g[i] = gamma[c] * invstd[i];
+        k1[i] = train ? sums[c] * inv_m : 0.f;
+        k2[i] = train ? sums[C + c] * inv_m : 0.f;
+    }
+    if (blockIdx.x == 0 && rl == 0 && dgamma) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dbeta[cv * 8 + i] = sums[cv * 8 + i];
+            dgamma[cv * 8 + i] = sums[C + cv * 8 + i];
+        }
+    }
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
+        const long long off = r * C + cv * 8;
+        float d[8], yy[8];
+        unpack8(ld8(dz + off), d);
+        unpack8(ld8(y + off), yy);
+        if (relu) {
+            float zz[8];
+            unpack8(ld8(z + off), zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) d[i] = 0.f;
+        }
+        if (dres) st8(dres + off, pack8(d));
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xh = (yy[i] - mean[i]) * invstd[i];
+            o[i] = g[i] * (d[i] - k1[i] - xh * k2[i]);
+        }
+        st8(dy + off, pack8(o));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row, D <= 1024, D % 8 == 0: row kept in registers (<= 4 vectors of 8 per lane).
+constexpr int LN_MAXV = 4;
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ y,
+                                                        float* __restrict__ stats, long long rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int nvec = D >> 3;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        float v[LN_MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+                unpack8(ld8(x + row * D + vi * 8), v[k]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s += v[k][i];
+            }
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+                float o[8];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
+                st8(y + row * D + vi * 8, pack8(o));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                            bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, long long rows, int D) {
+    extern __shared__ float sh[];   // [2][D] block partials of dgamma / dbeta
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int nvec = D >> 3;
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    float ag[LN_MAXV][8], ab[LN_MAXV][8];
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ag[k][i] = ab[k][i] = 0.f;
+
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+        float xh[LN_MAXV][8], dxh[LN_MAXV][8];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+                float xv[8], dv[8];
+                unpack8(ld8(x + row * D + vi * 8), xv);
+                unpack8(ld8(dy + row * D + vi * 8), dv);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[k][i] = (xv[i] - mean) * rstd;
+                    dxh[k][i] = dv[i] * gg[i];
+                    c1 += dxh[k][i];
+                    c2 += dxh[k][i] * xh[k][i];
+                    ag[k][i] += dv[i] * xh[k][i];
+                    ab[k][i] += dv[i];
+                }
+            }
+        }
+        c1 = warp_sum(c1) / (float)D;
+        c2 = warp_sum(c2) / (float)D;
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rstd * (dxh[k][i] - c1 - xh[k][i] * c2);
+                st8(dx + row * D + vi * 8, pack8(o));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(&sh[vi * 8 + i], ag[k][i]);
+                atomicAdd(&sh[D + vi * 8 + i], ab[k][i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        atomicAdd(dgamma + i, sh[i]);
+        atomicAdd(dbeta + i, sh[D + i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ row softmax
+// One warp per row of n <= 256 scores (row stride ld, pad columns [n, ld) written as zero).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ s, bf16* __restrict__ p, long long rows,
+                                                           int n, long long ld) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float v[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + k * 32;
+            v[k] = (c < n) ? __bfloat162float(s[row * ld + c]) : -INFINITY;
+            mx = fmaxf(mx, v[k]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + k * 32;
+            v[k] = (c < n) ? __expf(v[k] - mx) : 0.f;
+            sum += v[k];
+        }
+        const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + k * 32;
+            if (c < ld) p[row * ld + c] = __float2bfloat16(v[k] * inv);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __restrict__ p, const bf16* __restrict__ dp,
+                                                               bf16* __restrict__ ds, long long rows, int n, long long ld,
+                                                               float scale) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float pv[8], dv[8];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + k * 32;
+            pv[k] = (c < n) ? __bfloat162float(p[row * ld + c]) : 0.f;
+            dv[k] = (c < n) ? __bfloat162float(dp[row * ld + c]) : 0.f;
+            dot += pv[k] * dv[k];
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + k * 32;
+            if (c < ld) ds[row * ld + c] = __float2bfloat16(pv[k] * (dv[k] - dot) * scale);
+        }
+    }
+}
+
+bool bn_shape_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0; }
+
+}  // namespace
+
+extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, void* stream) {
+    DFU_CHECK_ARG(y && sums && M > 0 && bn_shape_ok(C), "dfu_bn_stats: unsupported shape M=%lld C=%d", (long long)M, C);
+    const int rpi = 256 / (C / 8);
+    bn_reduce_kernel<0><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)y, nullptr, nullptr, nullptr, sums, M, C, 0);
+    DFU_CHECK_LAUNCH("bn_stats");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_finalize(const float* sums, float* mean_invstd, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, int64_t M, int32_t C, float eps, float momentum, void* stream) {
+    DFU_CHECK_ARG(sums && mean_invstd && M > 0 && C > 0, "dfu_bn_finalize: bad args");
+    bn_finalize_kernel<<<dfu_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, mean_invstd, running_mean, running_var,
+                                                                          (long long*)num_batches_tracked, M, C, eps, momentum);
+    DFU_CHECK_LAUNCH("bn_finalize");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_eval_stats(const float* running_mean, const float* running_var, float* mean_invstd, int32_t C,
+                                 float eps, void* stream) {
+    DFU_CHECK_ARG(running_mean && running_var && mean_invstd && C > 0, "dfu_bn_eval_stats: bad args");
+    bn_eval_stats_kernel<<<dfu_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, mean_invstd, C, eps);
+    DFU_CHECK_LAUNCH("bn_eval_stats");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
+                            void* z, int64_t M, int32_t C, int32_t relu, void* stream) {
+    DFU_CHECK_ARG(y && mean_invstd && gamma && beta && z && M > 0 && bn_shape_ok(C), "dfu_bn_apply: unsupported shape M=%lld C=%d",
+                  (long long)M, C);
+    const int rpi = 256 / (C / 8);
+    bn_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu);
+    DFU_CHECK_LAUNCH("bn_apply");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, float* sums,
+                                 int64_t M, int32_t C, int32_t relu, void* stream) {
+    DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z), "dfu_bn_bwd_reduce: bad args");
+    const int rpi = 256 / (C / 8);
+    bn_reduce_kernel<1><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, sums, M, C, relu);
+    DFU_CHECK_LAUNCH("bn_bwd_reduce");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+                                const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int32_t C,
+                                int32_t relu, int32_t train, void* stream) {
+    DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z),
+                  "dfu_bn_bwd_apply: bad args");
+    const int rpi = 256 / (C / 8);
+    bn_bwd_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta, M,
+        C, relu, train);
+    DFU_CHECK_LAUNCH("bn_bwd_apply");
+    return DFU_OK;
+}
+
+extern "C" int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
+                             int32_t D, float eps, void* stream) {
+    DFU_CHECK_ARG(x && gamma && beta && y && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256, "dfu_layernorm: unsupported D=%d", D);
+    layernorm_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
+                                                                                   stats, rows, D, eps);
+    DFU_CHECK_LAUNCH("layernorm");
+    return DFU_OK;
+}
+extern "C" int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, void* dx,
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream) {
+    DFU_CHECK_ARG(dy && x && gamma && stats && dx && dgamma && dbeta && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256,
+                  "dfu_layernorm_bwd: unsupported D=%d", D);
+    layernorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 4), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+        (const bf16*)dy, (const bf16*)x, gamma, stats, (bf16*)dx, dgamma, dbeta, rows, D);
+    DFU_CHECK_LAUNCH("layernorm_bwd");
+    return DFU_OK;
+}
+
+extern "C" int dfu_softmax_rows(const void* s, void* p, int64_t rows, int32_t n, int64_t ld, void* stream) {
+    DFU_CHECK_ARG(s && p && rows > 0 && n > 0 && n <= 256 && ld >= n && ld <= 256, "dfu_softmax_rows: unsupported n=%d ld=%lld", n,
+                  (long long)ld);
+    softmax_rows_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)s, (bf16*)p, rows, n, ld);
+    DFU_CHECK_LAUNCH("softmax_rows");
+    return DFU_OK;
+}
+extern "C" int dfu_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int32_t n, int64_t ld, float scale,
+                                    void* stream) {
+    DFU_CHECK_ARG(p && dp && ds && rows > 0 && n > 0 && n <= 256 && ld >= n && ld <= 256, "dfu_softmax_rows_bwd: unsupported n=%d", n);
+    softmax_rows_bwd_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)p, (const bf16*)dp,
+                                                                                          (bf16*)ds, rows, n, ld, scale);
+    DFU_CHECK_LAUNCH("softmax_rows_bwd");
+    return DFU_OK;
+}

@@ -1,0 +1,461 @@
+// Elementwise / small reduction kernels: ReLU, add, GELU backward, bias-gradient column sums, strided copies,
+// dtype casts, dropout, ViT token assembly, pooling.  128-bit accesses, grid-stride loops.
+#include "common.cuh"
+#include "../../include/dfu_b200.h"
+
+namespace {
+
+inline int grid_for(long long items, int threads, int per_sm = 8) {
+    long long blocks = (items + threads - 1) / threads;
+    long long cap = (long long)dfu_num_sms() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+#define GRID_STRIDE(i, n) \
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+// OP: 0 relu, 1 relu_bwd(a=dy, b=y), 2 add, 3 gelu_bwd(a=dy, b=h)
+template <int OP>
+__global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                     bf16* __restrict__ out, long long n) {
+    const long long nv = n >> 3;
+    GRID_STRIDE(i, nv) {
+        float x[8], y[8], o[8];
+        unpack8(ld8(a + i * 8), x);
+        if (OP != 0) unpack8(ld8(b + i * 8), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (OP == 0) o[j] = fmaxf(x[j], 0.f);
+            else if (OP == 1) o[j] = (y[j] > 0.f) ? x[j] : 0.f;
+            else if (OP == 2) o[j] = x[j] + y[j];
+            else o[j] = x[j] * gelu_erf_grad(y[j]);
+        }
+        st8(out + i * 8, pack8(o));
+    }
+    // tail
+    if (blockIdx.x == 0) {
+        for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) {
+            const float x = __bfloat162float(a[i]);
+            const float y = (OP != 0) ? __bfloat162float(b[i]) : 0.f;
+            float o;
+            if (OP == 0) o = fmaxf(x, 0.f);
+            else if (OP == 1) o = (y > 0.f) ? x : 0.f;
+            else if (OP == 2) o = x + y;
+            else o = x * gelu_erf_grad(y);
+            out[i] = __float2bfloat16(o);
+        }
+    }
+}
+
+// Column sums of x[M, N] (row stride ld) added into out[N].  Block = 32 column-vectors x 8 row lanes.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M, int N,
+                                                     long long ld, int rows_per_block) {
+    __shared__ float red[8][32][9];
+    const int cvl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int cv = blockIdx.x * 32 + cvl;              // column vector (8 columns)
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, M);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (cv * 8 < N) {
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            float f[8];
+            unpack8(ld8(x + r * ld + cv * 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][cvl][i] = acc[i];
+    __syncthreads();
+    const int c = threadIdx.x;                         // 256 columns per block
+    const int col = blockIdx.x * 256 + c;
+    if (col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][c >> 3][c & 7];
+        atomicAdd(out + col, t);
+    }
+}
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M,
+                                                            int N, long long ld) {
+    // small / unaligned N: one thread per column, rows split over blockIdx.y
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    float t = 0.f;
+    for (long long r = blockIdx.y; r < M; r += gridDim.y) t += __bfloat162float(x[r * ld + col]);
+    atomicAdd(out + col, t);
+}
+
+__global__ void __launch_bounds__(256) copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst,
+                                                     long long ldd, long long rows, int cols, int vec) {
+    if (vec) {
+        const int cv = cols >> 3;
+        GRID_STRIDE(t, rows * cv) {
+            const long long r = t / cv;
+            const int v = (int)(t % cv);
+            st8(dst + r * ldd + v * 8, ld8(src + r * lds + v * 8));
+        }
+    } else {
+        GRID_STRIDE(t, rows * cols) {
+            const long long r = t / cols;
+            const int c = (int)(t % cols);
+            dst[r * ldd + c] = src[r * lds + c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                            long long rows, int cols, long long ldo) {
+    GRID_STRIDE(t, rows * ldo) {
+        const long long r = t / ldo;
+        const int c = (int)(t % ldo);
+        dst[t] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) cast_f32_bf16_flat_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                                 long long n) {
+    const long long nv = n >> 3;
+    GRID_STRIDE(i, nv) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i * 2);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + i * 2 + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        st8(dst + i * 8, pack8(f));
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+    GRID_STRIDE(i, n) dst[i] = __bfloat162float(src[i]);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                      uint8_t* __restrict__ mask, long long n, float p,
+                                                      const unsigned long long* __restrict__ seed_dev,
+                                                      unsigned long long stream_id) {
+    const uint64_t seed = seed_dev ? *seed_dev : 0ull;
+    const float inv_keep = 1.f / (1.f - p);
+    GRID_STRIDE(i, n) {
+        const uint64_t h = splitmix64(seed * 0x100000001B3ull + stream_id * 0x9E3779B1ull + (uint64_t)i);
+        const float u = (float)(h >> 40) * (1.f / 16777216.f);
+        const uint8_t keep = u >= p;
+        mask[i] = keep;
+        y[i] = __float2bfloat16(keep ? __bfloat162float(x[i]) * inv_keep : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                          bf16* __restrict__ dx, long long n, float p) {
+    const float inv_keep = 1.f / (1.f - p);
+    GRID_STRIDE(i, n) dx[i] = __float2bfloat16(mask[i] ? __bfloat162float(dy[i]) * inv_keep : 0.f);
+}
+__global__ void tick_u64_kernel(unsigned long long* c) { *c += 1ull; }
+
+// ViT token assembly (timm VisionTransformer._pos_embed): cls + pos, patches + pos.
+__global__ void __launch_bounds__(256) vit_assemble_kernel(const bf16* __restrict__ patch_out, const float* __restrict__ cls,
+                                                           const float* __restrict__ pos, bf16* __restrict__ tokens, int B,
+                                                           int T, int D) {
+    const int dv = D >> 3;
+    GRID_STRIDE(t, (long long)B * T * dv) {
+        const int v = (int)(t % dv);
+        const long long row = t / dv;
+        const int tok = (int)(row % T);
+        const int b = (int)(row / T);
+        float f[8];
+        if (tok == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = cls[v * 8 + i];
+        } else {
+            unpack8(ld8(patch_out + ((long long)b * (T - 1) + tok - 1) * D + v * 8), f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += pos[(long long)tok * D + v * 8 + i];
+        st8(tokens + row * D + v * 8, pack8(f));
+    }
+}
+// adjoint: thread per (token, 8-channel vector); loops over the batch for dpos/dcls (no atomics), writes dpatch.
+__global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const bf16* __restrict__ dtok, bf16* __restrict__ dpatch,
+                                                               float* __restrict__ dcls, float* __restrict__ dpos, int B,
+                                                               int T, int D) {
+    const int dv = D >> 3;
+    GRID_STRIDE(t, (long long)T * dv) {
+        const int v = (int)(t % dv);
+        const int tok = (int)(t / dv);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const bf16x8 raw = ld8(dtok + ((long long)b * T + tok) * D + v * 8);
+            float f[8];
+            unpack8(raw, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            if (tok > 0 && dpatch) st8(dpatch + ((long long)b * (T - 1) + tok - 1) * D + v * 8, raw);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dpos[(long long)tok * D + v * 8 + i] += acc[i];
+            if (tok == 0) dcls[v * 8 + i] += acc[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ pooling
+__global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                      uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+    const int cv = C >> 3;
+    GRID_STRIDE(t, (long long)B * Ho * Wo * cv) {
+        const int v = (int)(t % cv);
+        const long long pix = t / cv;
+        const int wo = (int)(pix % Wo);
+        const int ho = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+        float best[8];
+        uint8_t bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 255; }
+        for (int r = 0; r < 3; ++r) {
+            const int h = ho * 2 - 1 + r;
+            if (h < 0 || h >= H) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int w = wo * 2 - 1 + s;
+                if (w < 0 || w >= W) continue;
+                float f[8];
+                unpack8(ld8(x + (((long long)b * H + h) * W + w) * C + v * 8), f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (f[i] > best[i] || bi[i] == 255) { best[i] = f[i]; bi[i] = (uint8_t)(r * 3 + s); }
+            }
+        }
+        st8(y + pix * C + v * 8, pack8(best));
+        if (idx) {
+            uint2 packed;
+            packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((uint32_t)bi[3] << 24);
+            packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((uint32_t)bi[7] << 24);
+            *reinterpret_cast<uint2*>(idx + pix * C + v * 8) = packed;
+        }
+    }
+}
+// gather form: input pixel (h,w) is tap (r,s) of window (ho,wo) iff h = 2ho-1+r, w = 2wo-1+s.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dy,
+                                                          bf16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
+    const int cv = C >> 3;
+    GRID_STRIDE(t, (long long)B * H * W * cv) {
+        const int v = (int)(t % cv);
+        const long long pix = t / cv;
+        const int w = (int)(pix % W);
+        const int h = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long long)W * H));
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int r = 0; r < 3; ++r) {
+            const int hn = h + 1 - r;
+            if (hn < 0 || (hn & 1)) continue;
+            const int ho = hn >> 1;
+            if (ho >= Ho) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int wn = w + 1 - s;
+                if (wn < 0 || (wn & 1)) continue;
+                const int wo = wn >> 1;
+                if (wo >= Wo) continue;
+                const long long op = ((long long)b * Ho + ho) * Wo + wo;
+                const uint2 packed = *reinterpret_cast<const uint2*>(idx + op * C + v * 8);
+                float g[8];
+                unpack8(ld8(dy + op * C + v * 8), g);
+                const uint8_t tap = (uint8_t)(r * 3 + s);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t word = (i < 4) ? packed.x : packed.y;
+                    const uint8_t bi = (word >> ((i & 3) * 8)) & 0xFF;
+                    if (bi == tap) acc[i] += g[i];
+                }
+            }
+        }
+        st8(dx + pix * C + v * 8, pack8(acc));
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int HW, int C,
+                                                      long long ldo) {
+    const int cv = C >> 3;
+    GRID_STRIDE(t, (long long)B * cv) {
+        const int v = (int)(t % cv);
+        const int b = (int)(t / cv);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int p = 0; p < HW; ++p) {
+            float f[8];
+            unpack8(ld8(x + ((long long)b * HW + p) * C + v * 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= inv;
+        st8(out + (long long)b * ldo + v * 8, pack8(acc));
+    }
+}
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const bf16* __restrict__ dout, long long ldo, bf16* __restrict__ dx,
+                                                          int B, int HW, int C) {
+    const int cv = C >> 3;
+    const float inv = 1.f / (float)HW;
+    GRID_STRIDE(t, (long long)B * HW * cv) {
+        const int v = (int)(t % cv);
+        const long long q = t / cv;
+        const int b = (int)(q / HW);
+        float f[8];
+        unpack8(ld8(dout + (long long)b * ldo + v * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= inv;
+        st8(dx + q * C + v * 8, pack8(f));
+    }
+}
+
+bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int OP>
+int launch_binary(const void* a, const void* b, void* out, long long n, void* stream, const char* name) {
+    DFU_CHECK_ARG(a && out && n > 0 && (OP == 0 || b), "%s: bad args", name);
+    DFU_CHECK_ARG(al16(a) && al16(out) && (OP == 0 || al16(b)), "%s: buffers must be 16-byte aligned", name);
+    binary_kernel<OP><<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+    DFU_CHECK_LAUNCH(name);
+    return DFU_OK;
+}
+
+}  // namespace
+
+extern "C" int dfu_relu(const void* x, void* y, int64_t n, void* stream) { return launch_binary<0>(x, nullptr, y, n, stream, "dfu_relu"); }
+extern "C" int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
+    return launch_binary<1>(dy, y, dx, n, stream, "dfu_relu_bwd");
+}
+extern "C" int dfu_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+    return launch_binary<2>(a, b, out, n, stream, "dfu_add");
+}
+extern "C" int dfu_gelu_bwd(const void* dy, const void* h, void* dx, int64_t n, void* stream) {
+    return launch_binary<3>(dy, h, dx, n, stream, "dfu_gelu_bwd");
+}
+
+extern "C" int dfu_colsum(const void* x, float* out, int64_t M, int32_t N, int64_t ld, void* stream) {
+    DFU_CHECK_ARG(x && out && M > 0 && N > 0 && ld >= N, "dfu_colsum: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N % 8 == 0 && ld % 8 == 0 && al16(x)) {
+        const int col_blocks = dfu_cdiv(N, 256);
+        long long row_blocks = dfu_num_sms() * 4 / col_blocks + 1;
+        if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
+        if (row_blocks < 1) row_blocks = 1;
+        const int rows_per_block = (int)((M + row_blocks - 1) / row_blocks);
+        dim3 grid(col_blocks, dfu_cdiv(M, rows_per_block));
+        colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, out, M, N, ld, rows_per_block);
+    } else {
+        dim3 grid(dfu_cdiv(N, 64), (unsigned)(M < 256 ? M : 256));
+        colsum_scalar_kernel<<<grid, 64, 0, st>>>((const bf16*)x, out, M, N, ld);
+    }
+    DFU_CHECK_LAUNCH("dfu_colsum");
+    return DFU_OK;
+}
+
+extern "C" int dfu_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream) {
+    DFU_CHECK_ARG(src && dst && rows > 0 && cols > 0, "dfu_copy2d: bad args");
+    const int vec = (cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && al16(src) && al16(dst)) ? 1 : 0;
+    const long long items = vec ? rows * (cols / 8) : rows * cols;
+    copy2d_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, vec);
+    DFU_CHECK_LAUNCH("dfu_copy2d");
+    return DFU_OK;
+}
+
+extern "C" int dfu_cast_f32_bf16(const float* src, void* dst, int64_t rows, int32_t cols, int64_t ldo, void* stream) {
+    DFU_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ldo >= cols, "dfu_cast_f32_bf16: bad args");
+    if (ldo == cols && al16(src) && al16(dst)) {
+        const long long n = rows * cols;
+        cast_f32_bf16_flat_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+    } else {
+        cast_f32_bf16_kernel<<<grid_for(rows * ldo, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, rows, cols, ldo);
+    }
+    DFU_CHECK_LAUNCH("dfu_cast_f32_bf16");
+    return DFU_OK;
+}
+extern "C" int dfu_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+    DFU_CHECK_ARG(src && dst && n > 0, "dfu_cast_bf16_f32: bad args");
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+    DFU_CHECK_LAUNCH("dfu_cast_bf16_f32");
+    return DFU_OK;
+}
+
+extern "C" int dfu_dropout(const void* x, void* y, uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev,
+                           uint64_t stream_id, void* stream) {
+    DFU_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dfu_dropout: bad args (p=%f)", p);
+    dropout_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, mask, n, p,
+                                                                      (const unsigned long long*)seed_dev, stream_id);
+    DFU_CHECK_LAUNCH("dfu_dropout");
+    return DFU_OK;
+}
+extern "C" int dfu_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, void* stream) {
+    DFU_CHECK_ARG(dy && mask && dx && n > 0 && p >= 0.f && p < 1.f, "dfu_dropout_bwd: bad args");
+    dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, mask, (bf16*)dx, n, p);
+    DFU_CHECK_LAUNCH("dfu_dropout_bwd");
+    return DFU_OK;
+}
+extern "C" int dfu_tick_u64(uint64_t* counter, void* stream) {
+    DFU_CHECK_ARG(counter, "dfu_tick_u64: null");
+    tick_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)counter);
+    DFU_CHECK_LAUNCH("dfu_tick_u64");
+    return DFU_OK;
+}
+
+extern "C" int dfu_vit_assemble(const void* patch_out, const float* cls, const float* pos, void* tokens, int32_t B, int32_t T,
+                                int32_t D, void* stream) {
+    DFU_CHECK_ARG(patch_out && cls && pos && tokens && B > 0 && T > 1 && D % 8 == 0, "dfu_vit_assemble: bad args");
+    vit_assemble_kernel<<<grid_for((long long)B * T * (D / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)patch_out, cls, pos, (bf16*)tokens, B, T, D);
+    DFU_CHECK_LAUNCH("dfu_vit_assemble");
+    return DFU_OK;
+}
+extern "C" int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dcls, float* dpos, int32_t B, int32_t T,
+                                    int32_t D, void* stream) {
+    DFU_CHECK_ARG(dtokens && dcls && dpos && B > 0 && T > 1 && D % 8 == 0, "dfu_vit_assemble_bwd: bad args");
+    vit_assemble_bwd_kernel<<<grid_for((long long)T * (D / 8), 64, 32), 64, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dtokens, (bf16*)dpatch, dcls, dpos, B, T, D);
+    DFU_CHECK_LAUNCH("dfu_vit_assemble_bwd");
+    return DFU_OK;
+}
+
+extern "C" int dfu_maxpool3x3s2(const void* x, void* y, uint8_t* idx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+    DFU_CHECK_ARG(x && y && B > 0 && C % 8 == 0, "dfu_maxpool3x3s2: bad args");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, idx,
+                                                                                                     B, H, W, C, Ho, Wo);
+    DFU_CHECK_LAUNCH("dfu_maxpool3x3s2");
+    return DFU_OK;
+}
+extern "C" int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
+                                    void* stream) {
+    DFU_CHECK_ARG(idx && dy && dx && B > 0 && C % 8 == 0, "dfu_maxpool3x3s2_bwd: bad args");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    maxpool_bwd_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(idx, (const bf16*)dy,
+                                                                                                       (bf16*)dx, B, H, W, C, Ho, Wo);
+    DFU_CHECK_LAUNCH("dfu_maxpool3x3s2_bwd");
+    return DFU_OK;
+}
+extern "C" int dfu_avgpool(const void* x, void* out, int32_t B, int32_t HW, int32_t C, int64_t ldo, void* stream) {
+    DFU_CHECK_ARG(x && out && B > 0 && HW > 0 && C % 8 == 0 && ldo % 8 == 0 && al16(out), "dfu_avgpool: bad args");
+    avgpool_kernel<<<grid_for((long long)B * (C / 8), 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, B, HW, C, ldo);
+    DFU_CHECK_LAUNCH("dfu_avgpool");
+    return DFU_OK;
+}
+extern "C" int dfu_avgpool_bwd(const void* dout, int64_t ldo, void* dx, int32_t B, int32_t HW, int32_t C, void* stream) {
+    DFU_CHECK_ARG(dout && dx && B > 0 && HW > 0 && C % 8 == 0 && ldo % 8 == 0 && al16(dout), "dfu_avgpool_bwd: bad args");
+    avgpool_bwd_kernel<<<grid_for((long long)B * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, ldo, (bf16*)dx,
+                                                                                                    B, HW, C);
+    DFU_CHECK_LAUNCH("dfu_avgpool_bwd");
+    return DFU_OK;
+}

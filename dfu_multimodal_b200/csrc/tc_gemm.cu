@@ -1,0 +1,576 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the one dense-contraction kernel behind every Linear and
+// (im2col'ed) convolution of the fusion step, forward, dgrad and wgrad.
+//
+//   D[z][m][n] = act(alpha * sum_k A[z][m][k] * B[z][n][k] + bias[n]) + res[z][m][n]
+//
+// Persistent, warp-specialised:
+//   warp 0      TMA producer (one lane): 4-stage ring of {A 128x64, B block_n x64} bf16 tiles, SWIZZLE_128B
+//   warp 1      MMA issuer (one lane): tcgen05.mma cta_group::1 kind::f16, M=128, N=block_n, K=16 x4 per stage
+//   warp 2      TMEM allocator (512 columns = two 128 x 256 fp32 accumulators, double buffered)
+//   warps 4-11  epilogue: tcgen05.ld 32x32b.x32 -> bias / act / residual -> 128-bit global stores
+// Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), so
+// dgrad (B MN-major) and wgrad (A and B MN-major) need no transposed copies.  Split-K (fp32 atomic
+// accumulation) keeps all SMs busy on the skinny wgrad shapes.
+#include "common.cuh"
+#include "../../include/dfu_b200.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one swizzle row
+constexpr int MAX_BLOCK_N = 256;
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
+constexpr int B_TILE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;   // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;    // + alignment slack
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+
+struct GemmParams {
+    int M, N, K;
+    int nb0, nb1;
+    int block_n;
+    int a_mn, b_mn;
+    int split_k, num_kb, kb_per_split;
+    int m_tiles, n_tiles;
+    long long total_work;
+    void* D;
+    long long ldd, sd0, sd1;
+    int d_fp32, atomic;
+    bf16* aux;
+    const float* bias;
+    const bf16* res;
+    long long ldr, sr0, sr1;
+    float alpha;
+    int act;
+    int vec_ok;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ----------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t tmem_full_bar[2];
+    __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    if (warp_idx == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp_idx == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const uint32_t stage_tx = A_TILE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+                long long t = w;
+                const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
+                const int m_tile = (int)(t % p.m_tiles); t /= p.m_tiles;
+                const int ks = (int)(t % p.split_k); t /= p.split_k;
+                const int z0 = (int)(t % p.nb0);
+                const int z1 = (int)(t / p.nb0);
+                const int m0 = m_tile * BLOCK_M, n0 = n_tile * p.block_n;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_TILE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], stage_tx);
+                    const int k0 = kb * BLOCK_K;
+                    if (!p.a_mn) {
+                        tma_load_4d(&map_a, &full_bar[stage], sa, k0, m0, z0, z1);
+                    } else {
+                        tma_load_4d(&map_a, &full_bar[stage], sa, m0, k0, z0, z1);
+                        tma_load_4d(&map_a, &full_bar[stage], sa + 8192, m0 + 64, k0, z0, z1);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, z0, z1);
+                    } else {
+                        for (int j = 0; j < p.block_n / 64; ++j)
+                            tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, n0 + j * 64, k0, z0, z1);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ MMA issuer
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) |
+                                   ((uint32_t)p.b_mn << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+                long long t = w / ((long long)p.n_tiles * p.m_tiles);
+                const int ks = (int)(t % p.split_k);
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        const uint64_t adesc = p.a_mn ? make_desc(sa + k * 2048, 8192, 1024)
+                                                      : make_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = p.b_mn ? make_desc(sb + k * 2048, 8192, 1024)
+                                                      : make_desc(sb + k * 32, 16, 1024);
+                        tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp_idx >= EPI_WARP0) {
+        // ---------------------------------------------------------------------- epilogue
+        const int ew = warp_idx - EPI_WARP0;
+        const int quarter = warp_idx & 3;        // TMEM lane quarter this warp may touch
+        const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
+        const int n_chunks = p.block_n / 32;
+        int it = 0;
+        for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+            long long t = w;
+            const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
+            const int m_tile = (int)(t % p.m_tiles); t /= p.m_tiles;
+            t /= p.split_k;
+            const int z0 = (int)(t % p.nb0);
+            const int z1 = (int)(t / p.nb0);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const int m = m_tile * BLOCK_M + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const long long d_off = (long long)z1 * p.sd1 + (long long)z0 * p.sd0 + (long long)m * p.ldd;
+            const long long r_off = (long long)z1 * p.sr1 + (long long)z0 * p.sr0 + (long long)m * p.ldr;
+            for (int c = group; c < n_chunks; c += 2) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N + c * 32;
+                tmem_ld32(taddr, r);
+                tmem_ld_wait();
+                const int nbase = n_tile * p.block_n + c * 32;
+                if (nbase >= p.N) continue;      // warp-uniform
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int n = nbase + g * 8;
+                    if (n >= p.N) break;         // warp-uniform
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+                    const bool full8 = (n + 8 <= p.N);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                    }
+                    if (!row_ok) continue;
+                    if (p.aux) {
+                        bf16* ap = p.aux + d_off + n;
+                        if (full8 && p.vec_ok) {
+                            st8(ap, pack8(v));
+                        } else {
+                            for (int j = 0; j < 8; ++j)
+                                if (n + j < p.N) ap[j] = __float2bfloat16(v[j]);
+                        }
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (p.res) {
+                        const bf16* rp = p.res + r_off + n;
+                        if (full8 && p.vec_ok) {
+                            float rv[8];
+                            unpack8(ld8(rp), rv);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] += rv[j];
+                        } else {
+                            for (int j = 0; j < 8; ++j)
+                                if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (p.d_fp32) {
+                        float* dp = reinterpret_cast<float*>(p.D) + d_off + n;
+                        if (p.atomic == 2) {          // split-K partial sums
+                            if (full8 && p.vec_ok) {
+                                red_add_v4(dp, v[0], v[1], v[2], v[3]);
+                                red_add_v4(dp + 4, v[4], v[5], v[6], v[7]);
+                            } else {
+                                for (int j = 0; j < 8; ++j)
+                                    if (n + j < p.N) atomicAdd(dp + j, v[j]);
+                            }
+                        } else if (p.atomic == 1) {   // sole owner of the tile: plain read-modify-write
+                            if (full8 && p.vec_ok) {
+                                float4 o0 = *reinterpret_cast<float4*>(dp), o1 = *reinterpret_cast<float4*>(dp + 4);
+                                *reinterpret_cast<float4*>(dp) = make_float4(o0.x + v[0], o0.y + v[1], o0.z + v[2], o0.w + v[3]);
+                                *reinterpret_cast<float4*>(dp + 4) = make_float4(o1.x + v[4], o1.y + v[5], o1.z + v[6], o1.w + v[7]);
+                            } else {
+                                for (int j = 0; j < 8; ++j)
+                                    if (n + j < p.N) dp[j] += v[j];
+                            }
+                        } else if (full8 && p.vec_ok) {
+                            *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            for (int j = 0; j < 8; ++j)
+                                if (n + j < p.N) dp[j] = v[j];
+                        }
+                    } else {
+                        bf16* dp = reinterpret_cast<bf16*>(p.D) + d_off + n;
+                        if (full8 && p.vec_ok) {
+                            st8(dp, pack8(v));
+                        } else {
+                            for (int j = 0; j < 8; ++j)
+                                if (n + j < p.N) dp[j] = __float2bfloat16(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------- SIMT check kernel
+// Straightforward fp32-accumulate GEMM over the same argument block: validates the tcgen05 kernel on the
+// device and serves shapes TMA cannot describe (row strides that are not multiples of 16 bytes, N < 32).
+struct RefParams {
+    int M, N, K, nb0, nb1;
+    const bf16* A; int a_mn; long long lda, sa0, sa1;
+    const bf16* B; int b_mn; long long ldb, sb0, sb1;
+    void* D; int d_fp32, atomic; long long ldd, sd0, sd1;
+    bf16* aux; const float* bias; const bf16* res; long long ldr, sr0, sr1;
+    float alpha; int act;
+};
+
+__global__ void __launch_bounds__(256) dfu_ref_gemm_kernel(const RefParams p) {
+    __shared__ float As[16][17];
+    __shared__ float Bs[16][17];
+    const int z = blockIdx.z;
+    const int z0 = z % p.nb0, z1 = z / p.nb0;
+    const bf16* A = p.A + z1 * p.sa1 + z0 * p.sa0;
+    const bf16* B = p.B + z1 * p.sb1 + z0 * p.sb0;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        {
+            const int am = blockIdx.y * 16 + ty, ak = k0 + tx;
+            float v = 0.f;
+            if (am < p.M && ak < p.K)
+                v = __bfloat162float(p.a_mn ? A[(long long)ak * p.lda + am] : A[(long long)am * p.lda + ak]);
+            As[ty][tx] = v;
+            const int bn = blockIdx.x * 16 + ty, bk = k0 + tx;
+            float u = 0.f;
+            if (bn < p.N && bk < p.K)
+                u = __bfloat162float(p.b_mn ? B[(long long)bk * p.ldb + bn] : B[(long long)bn * p.ldb + bk]);
+            Bs[ty][tx] = u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[tx][k];
+        __syncthreads();
+    }
+    if (m >= p.M || n >= p.N) return;
+    float v = acc * p.alpha;
+    if (p.bias) v += p.bias[n];
+    const long long d_off = z1 * p.sd1 + z0 * p.sd0 + (long long)m * p.ldd + n;
+    if (p.aux) p.aux[d_off] = __float2bfloat16(v);
+    if (p.act == 1) v = fmaxf(v, 0.f);
+    else if (p.act == 2) v = gelu_erf(v);
+    if (p.res) v += __bfloat162float(p.res[z1 * p.sr1 + z0 * p.sr0 + (long long)m * p.ldr + n]);
+    if (p.d_fp32) {
+        float* d = reinterpret_cast<float*>(p.D) + d_off;
+        if (p.atomic) atomicAdd(d, v); else *d = v;
+    } else {
+        reinterpret_cast<bf16*>(p.D)[d_off] = __float2bfloat16(v);
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+bool g_encode_tried = false;
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+        (void)cudaGetLastError();
+    }
+    return g_encode;
+}
+
+// 4-D bf16 tensor map {inner, rows, z0, z1}; strides in elements.
+int make_map(CUtensorMap* map, const void* base, long long inner, long long rows, long long ld, int nb0, long long s0,
+             int nb1, long long s1, int box_inner, int box_rows) {
+    auto enc = get_encode();
+    if (!enc) { dfu_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DFU_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
+    // strides of dims 1..3 in bytes (multiples of 16); a batch dim of extent 1 only ever sees coordinate 0
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb0 > 1 ? s0 : ld) * 2,
+                             (cuuint64_t)(nb1 > 1 ? s1 : ld) * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfu_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld box=%dx%d", (int)r, inner, rows,
+                      ld, box_inner, box_rows);
+        return DFU_ERR_CUDA;
+    }
+    return DFU_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int pick_block_n(int N, bool mn_major) {
+    const int step = mn_major ? 64 : 32;
+    int best = step, best_cost = 1 << 30;
+    for (int bn = step; bn <= MAX_BLOCK_N; bn += step) {
+        const int tiles = (N + bn - 1) / bn;
+        // cost ~ MMA columns issued (padding waste) + a per-tile overhead favouring fewer, larger tiles
+        const int cost = tiles * bn + tiles * 24;
+        if (cost <= best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DFU_CHECK_ARG(a != nullptr, "dfu_gemm: null args");
+    DFU_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->nb0 > 0 && a->nb1 > 0, "dfu_gemm: bad sizes M=%d N=%d K=%d",
+                  a->M, a->N, a->K);
+    DFU_CHECK_ARG(a->A && a->B && a->D, "dfu_gemm: null operand");
+    DFU_CHECK_ARG(!(a->accumulate && a->d_dtype != 1), "dfu_gemm: accumulate needs fp32 output");
+    DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias)),
+                  "dfu_gemm: accumulate mode takes no bias/act/res/aux");
+
+    const bool batched = (a->nb0 * a->nb1) > 1;
+    bool tma_ok = aligned16(a->A) && aligned16(a->B) && (a->lda % 8 == 0) && (a->ldb % 8 == 0);
+    if (batched)
+        tma_ok = tma_ok && (a->nb0 == 1 || (a->sa0 % 8 == 0 && a->sb0 % 8 == 0)) &&
+                 (a->nb1 == 1 || (a->sa1 % 8 == 0 && a->sb1 % 8 == 0));
+    const bool tiny = a->N < 16;
+    int impl = a->impl;
+    if (impl == 0 && (!tma_ok || tiny)) impl = 1;   // shape-specialised SIMT kernel, same semantics
+
+    if (impl == 1) {
+        RefParams p;
+        p.M = a->M; p.N = a->N; p.K = a->K; p.nb0 = a->nb0; p.nb1 = a->nb1;
+        p.A = (const bf16*)a->A; p.a_mn = a->a_major; p.lda = a->lda; p.sa0 = a->sa0; p.sa1 = a->sa1;
+        p.B = (const bf16*)a->B; p.b_mn = a->b_major; p.ldb = a->ldb; p.sb0 = a->sb0; p.sb1 = a->sb1;
+        p.D = a->D; p.d_fp32 = a->d_dtype; p.atomic = a->accumulate; p.ldd = a->ldd; p.sd0 = a->sd0; p.sd1 = a->sd1;
+        p.aux = (bf16*)a->aux; p.bias = a->bias; p.res = (const bf16*)a->res; p.ldr = a->ldr; p.sr0 = a->sr0;
+        p.sr1 = a->sr1; p.alpha = a->alpha; p.act = a->act;
+        dim3 grid(dfu_cdiv(a->N, 16), dfu_cdiv(a->M, 16), a->nb0 * a->nb1);
+        DFU_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "dfu_gemm(simt): grid too large (M=%d, batch=%d)", a->M,
+                      a->nb0 * a->nb1);
+        dfu_ref_gemm_kernel<<<grid, 256, 0, stream>>>(p);
+        DFU_CHECK_LAUNCH("dfu_ref_gemm_kernel");
+        return DFU_OK;
+    }
+
+    GemmParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.nb0 = a->nb0; p.nb1 = a->nb1;
+    p.a_mn = a->a_major ? 1 : 0;
+    p.b_mn = a->b_major ? 1 : 0;
+    p.block_n = pick_block_n(a->N, p.b_mn);
+    p.m_tiles = dfu_cdiv(a->M, BLOCK_M);
+    p.n_tiles = dfu_cdiv(a->N, p.block_n);
+    p.num_kb = dfu_cdiv(a->K, BLOCK_K);
+    const int num_sms = dfu_num_sms();
+    const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
+    const long long out_tiles = (long long)p.m_tiles * p.n_tiles * a->nb0 * a->nb1;
+    int split = 1;
+    if (a->accumulate && out_tiles < max_ctas) {
+        split = (int)((2LL * max_ctas + out_tiles - 1) / out_tiles);
+        // keep at least 4 k-blocks per split so the pipeline amortises its fill
+        split = min(split, max(1, p.num_kb / 4));
+    }
+    p.kb_per_split = dfu_cdiv(p.num_kb, split);
+    p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
+    p.total_work = out_tiles * p.split_k;
+    p.D = a->D; p.ldd = a->ldd; p.sd0 = a->sd0; p.sd1 = a->sd1;
+    p.d_fp32 = a->d_dtype; p.atomic = a->accumulate ? (p.split_k > 1 ? 2 : 1) : 0;
+    p.aux = (bf16*)a->aux; p.bias = a->bias; p.res = (const bf16*)a->res;
+    p.ldr = a->ldr; p.sr0 = a->sr0; p.sr1 = a->sr1;
+    p.alpha = a->alpha; p.act = a->act;
+    const int esz = a->d_dtype ? 4 : 2;
+    bool vec = aligned16(a->D) && ((a->ldd * esz) % 16 == 0) && ((a->sd0 * esz) % 16 == 0) && ((a->sd1 * esz) % 16 == 0);
+    if (a->aux) vec = vec && aligned16(a->aux) && (a->ldd % 8 == 0) && (a->sd0 % 8 == 0) && (a->sd1 % 8 == 0);
+    if (a->res) vec = vec && aligned16(a->res) && (a->ldr % 8 == 0) && (a->sr0 % 8 == 0) && (a->sr1 % 8 == 0);
+    p.vec_ok = vec ? 1 : 0;
+
+    CUtensorMap map_a, map_b;
+    int rc;
+    if (!p.a_mn) rc = make_map(&map_a, a->A, a->K, a->M, a->lda, a->nb0, a->sa0, a->nb1, a->sa1, BLOCK_K, BLOCK_M);
+    else         rc = make_map(&map_a, a->A, a->M, a->K, a->lda, a->nb0, a->sa0, a->nb1, a->sa1, 64, BLOCK_K);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_map(&map_b, a->B, a->K, a->N, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, BLOCK_K, p.block_n);
+    else         rc = make_map(&map_b, a->B, a->N, a->K, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, 64, BLOCK_K);
+    if (rc) return rc;
+
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            dfu_set_error("dfu_gemm: cannot reserve %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return DFU_ERR_CUDA;
+        }
+        g_attr_set = true;
+    }
+    const int grid = (int)min((long long)max_ctas, p.total_work);
+    dfu_tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
+    DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
+    return DFU_OK;
+}

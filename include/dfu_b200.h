@@ -1,0 +1,188 @@
+/*
+ * dfu_b200.h -- C ABI of libdfu_b200.so: the sm_100a kernels behind the late-fusion DFU classifier step.
+ *
+ * The reference (ShreenathKR2000/DFU-Multimodal) has no FFI of its own: its hot path is the PyTorch
+ * nn.Module protocol (`model(rgb, thermal)`, `loss.backward()`, `optimizer.step()`;
+ * notebooks/train_multimodal_fusion.py:368-388) dispatching into ATen/cuDNN/cuBLAS.  Every entry point
+ * below replaces the ATen call named in its comment.  Conventions:
+ *   - plain pointers + sizes, no torch types; the CALLER owns every buffer, workspace included;
+ *   - all pointers are device pointers unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - no hidden allocation, no host synchronisation, re-entrant across streams;
+ *   - returns 0 on success; nonzero -> dfu_last_error() holds the reason (host side raises RuntimeError);
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point fails.
+ * Activations are bf16, NHWC for images ([B*H*W, C] row-major matrices) and [B*197, 768] for tokens;
+ * parameters, statistics, gradients of parameters and optimizer state are fp32.
+ */
+#ifndef DFU_B200_H
+#define DFU_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dfu_last_error(void);
+int dfu_version(void);
+/* 0 if the current CUDA device is sm_100 class and the driver TMA entry point resolved. */
+int dfu_device_ok(void);
+int dfu_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM: D[z][m][n] = act(alpha * sum_k A[z][m][k] * B[z][n][k] + bias[n]) + res[z][m][n]
+ * Replaces aten::addmm / aten::mm / aten::bmm (nn.Linear in timm ViT blocks and the fusion head,
+ * train_multimodal_fusion.py:305-313) and cudnn convolution fwd/dgrad/wgrad after im2col
+ * (torchvision ResNet, train_multimodal_fusion.py:294).
+ *   a_major/b_major: 0 = K-major (A is [M,K] row-major with row stride lda; B is [N,K] row-major),
+ *                    1 = MN-major (A stored [K,M] row-major with row stride lda; B stored [K,N]).
+ *   z = z1*nb0 + z0, element strides s?0 / s?1 per batch dim.  All strides in ELEMENTS.
+ *   d_dtype: 0 = bf16, 1 = fp32.  accumulate=1 (fp32 only): D += result (atomic, enables split-K).
+ *   aux (bf16, same geometry as D) receives the pre-activation value when non-null.
+ *   act: 0 none, 1 relu, 2 gelu(erf).  impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t M, N, K, nb0, nb1;
+    const void* A; int32_t a_major; int64_t lda, sa0, sa1;
+    const void* B; int32_t b_major; int64_t ldb, sb0, sb1;
+    void* D; int32_t d_dtype; int64_t ldd, sd0, sd1;
+    int32_t accumulate;
+    void* aux;
+    const float* bias;
+    const void* res; int64_t ldr, sr0, sr1;
+    float alpha;
+    int32_t act;
+    int32_t impl;
+    int32_t max_ctas; /* 0 = one per SM */
+} dfu_gemm_args;
+int dfu_gemm(const dfu_gemm_args* a, void* stream);
+
+/* ------------------------------- layout / preprocessing ------------------------------------ */
+/* a9: ToTensor+Normalize (train_multimodal_fusion.py:184-188,201-205) on uint8 HWC images.
+ * out NHWC bf16: out[b,h,w,c] = (in/255 - mean[c]) / std[c]. */
+int dfu_preprocess_u8_nhwc(const uint8_t* in, void* out, int64_t n_pixels, const float* mean3_host,
+                           const float* std3_host, void* stream);
+/* Same normalisation fused with ViT patch extraction: out[(b*196+p), c*256+i*16+j] (timm PatchEmbed order). */
+int dfu_preprocess_u8_patches(const uint8_t* in, void* out, int32_t B, const float* mean3_host,
+                              const float* std3_host, void* stream);
+/* fp32 NCHW (the nn.Module contract) -> bf16 NHWC, and its adjoint (grad wrt the input image). */
+int dfu_nchw_f32_to_nhwc_bf16(const float* in, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int dfu_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* fp32 NCHW 224x224x3 -> ViT patches bf16 [B*196,768], and adjoint. */
+int dfu_patchify_f32(const float* in, void* out, int32_t B, void* stream);
+int dfu_unpatchify_f32(const void* dpatches, float* dimg, int32_t B, void* stream);
+/* im2col on NHWC bf16: col[(b,ho,wo)][(r*S+s)*C+c], row stride ldc (>= R*S*C, pad columns zeroed). */
+int dfu_im2col_nhwc(const void* x, void* col, int32_t B, int32_t H, int32_t W, int32_t C, int32_t R, int32_t S,
+                    int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, int64_t ldc, void* stream);
+/* adjoint of im2col (gather form, deterministic). */
+int dfu_col2im_nhwc(const void* col, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t R, int32_t S,
+                    int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, int64_t ldc, void* stream);
+
+/* ------------------------------------ BatchNorm (a3) --------------------------------------- */
+/* Per-channel sum / sum of squares of y[M,C] (bf16) accumulated into sums[2*C] (fp32, caller zeroes). */
+int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, void* stream);
+/* mean/invstd from sums; running stats update (momentum, unbiased var) as torch BatchNorm2d in train(). */
+int dfu_bn_finalize(const float* sums, float* mean_invstd, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, int64_t M, int32_t C, float eps, float momentum, void* stream);
+/* eval(): mean/invstd from running stats. */
+int dfu_bn_eval_stats(const float* running_mean, const float* running_var, float* mean_invstd, int32_t C,
+                      float eps, void* stream);
+/* z = [relu]( gamma*(y-mean)*invstd + beta [+ res] ) */
+int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
+                 void* z, int64_t M, int32_t C, int32_t relu, void* stream);
+/* Backward pass 1: sums[0:C] += sum(dpre), sums[C:2C] += sum(dpre*xhat), dpre = dz*(z>0 if relu). */
+int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, float* sums,
+                      int64_t M, int32_t C, int32_t relu, void* stream);
+/* Backward pass 2: dy = gamma*invstd*(dpre - sum_dpre/M - xhat*sum_dpre_xhat/M); dres = dpre (optional);
+ * train=0 (eval BN): dy = gamma*invstd*dpre. dgamma/dbeta (fp32 [C]) written when non-null. */
+int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+                     const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int32_t C,
+                     int32_t relu, int32_t train, void* stream);
+
+/* ------------------------------------ pooling / pointwise ---------------------------------- */
+/* MaxPool2d(3, stride 2, pad 1) on NHWC bf16; idx (u8, same shape as y, may be null) records the winning tap
+ * (first maximum in row-major scan order, as ATen) for the backward gather. */
+int dfu_maxpool3x3s2(const void* x, void* y, uint8_t* idx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
+                         void* stream);
+/* global average pool [B,HW,C] -> [B, C] written with row stride ldo (lets it land inside the concat buffer) */
+int dfu_avgpool(const void* x, void* out, int32_t B, int32_t HW, int32_t C, int64_t ldo, void* stream);
+int dfu_avgpool_bwd(const void* dout, int64_t ldo, void* dx, int32_t B, int32_t HW, int32_t C, void* stream);
+int dfu_relu(const void* x, void* y, int64_t n, void* stream);
+int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+int dfu_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* dx = dy * gelu'(h) */
+int dfu_gelu_bwd(const void* dy, const void* h, void* dx, int64_t n, void* stream);
+/* column sums of a bf16 [M,N] matrix (row stride ld) added into out[N] fp32 (caller zeroes): bias gradients. */
+int dfu_colsum(const void* x, float* out, int64_t M, int32_t N, int64_t ld, void* stream);
+/* strided 2-D copy bf16 (rows x cols), used for concat / cls-token selection. */
+int dfu_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream);
+/* fp32 [rows, cols] (row stride cols) -> bf16 [rows, ldo], pad columns zeroed: weight shadow copies. */
+int dfu_cast_f32_bf16(const float* src, void* dst, int64_t rows, int32_t cols, int64_t ldo, void* stream);
+int dfu_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* Bernoulli keep-mask dropout (counter-based hash RNG): y = x*mask/(1-p); mask u8 saved for backward.
+ * The seed lives in device memory (advanced by dfu_tick_u64) so a captured CUDA graph draws fresh masks. */
+int dfu_dropout(const void* x, void* y, uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev,
+                uint64_t stream_id, void* stream);
+int dfu_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, void* stream);
+int dfu_tick_u64(uint64_t* counter, void* stream);
+
+/* ------------------------------------ ViT pieces (a4) -------------------------------------- */
+/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+p,:] = patch_out[b*196+p,:] + pos[1+p]  (timm _pos_embed) */
+int dfu_vit_assemble(const void* patch_out, const float* cls, const float* pos, void* tokens, int32_t B,
+                     int32_t T, int32_t D, void* stream);
+/* adjoint: dpatch = dtokens[:,1:], dcls += sum_b dtokens[b,0], dpos += sum_b dtokens[b] (fp32, caller zeroes) */
+int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dcls, float* dpos, int32_t B, int32_t T,
+                         int32_t D, void* stream);
+/* LayerNorm over the last dim (eps 1e-6 in timm): y bf16, stats[2*rows] = (mean, rstd) fp32. */
+int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
+                  int32_t D, float eps, void* stream);
+/* dx (bf16), dgamma/dbeta += (fp32, caller zeroes). */
+int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, void* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream);
+/* Row softmax of S[rows, ld] over the first n columns (fp32 math), pad columns written as 0. In place allowed. */
+int dfu_softmax_rows(const void* s, void* p, int64_t rows, int32_t n, int64_t ld, void* stream);
+/* dS = P * (dP - rowsum(dP*P)) * scale */
+int dfu_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int32_t n, int64_t ld, float scale,
+                         void* stream);
+/* ------------------------------------ loss (a6) -------------------------------------------- */
+/* Weighted CrossEntropyLoss (mean reduction: sum w[y]*nll / sum w[y]); weight may be null.
+ * logits fp32 [B,C]; labels int64; loss fp32 scalar; dlogits fp32 [B,C] = d loss / d logits. */
+int dfu_cross_entropy(const float* logits, const int64_t* labels, const float* weight, float* loss,
+                      float* dlogits, int32_t B, int32_t C, void* stream);
+/* softmax[:,1] and argmax (extended_metrics.py:636-637) */
+int dfu_predict(const float* logits, float* prob1, int64_t* pred, int32_t B, int32_t C, void* stream);
+/* out = a * (*scalar_dev): applies the upstream scalar gradient of the loss to dlogits. */
+int dfu_scale_by_scalar(const float* a, const float* scalar_dev, float* out, int64_t n, void* stream);
+
+/* ------------------------------------ optimizer (a8) --------------------------------------- */
+/* Multi-tensor AdamW (torch.optim.AdamW semantics, one group). `table` is a device array of n_tensors
+ * records {p, g, m, v, shadow_bf16(or 0), numel}; g may be fp32 or bf16 (g_bf16 flag);
+ * step is a device fp32 scalar holding the step count AFTER increment (kernel increments it itself
+ * via dfu_adamw_tick so the whole update is CUDA-graph capturable). */
+typedef struct {
+    float* p; const void* g; float* m; float* v; void* shadow; int64_t numel;
+} dfu_adamw_tensor;
+int dfu_adamw_tick(float* step, void* stream);
+int dfu_adamw(const dfu_adamw_tensor* table, int32_t n_tensors, const int32_t* chunk_tensor,
+              const int32_t* chunk_offset, int32_t n_chunks, int32_t chunk_size, const float* step, float lr,
+              float beta1, float beta2, float eps, float weight_decay, float grad_scale, int32_t g_bf16,
+              void* stream);
+/* Flat variant over one contiguous fp32 parameter arena. */
+int dfu_adamw_flat(float* p, const void* g, float* m, float* v, void* shadow, int64_t n, const float* step,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   int32_t g_bf16, void* stream);
+
+/* ------------------------------------ Grad-CAM (a11) / TTA (a12) --------------------------- */
+/* weights w_c = mean_hw G[c]; cam = relu(sum_{c<nc} w_c A[c]) / max (if max>0).
+ * A: [HW, CA] bf16 NHWC activations of one image, G: [HW, CG] bf16; cam fp32 [HW]. */
+int dfu_gradcam(const void* A, int32_t CA, const void* G, int32_t CG, int32_t HW, int32_t nc, float* cam,
+                void* stream);
+/* |dimg|.mean(C) / max  over a fp32 [3,H,W] input gradient -> [H*W] */
+int dfu_saliency(const float* dimg, float* out, float* max_scratch, int32_t C, int32_t HW, void* stream);
+/* TTA vote: probs [n, V] -> mean prob and majority vote (mean(p>0.5) > 0.5). */
+int dfu_tta_vote(const float* probs, float* mean_prob, int64_t* pred, int32_t n, int32_t V, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
