@@ -16,7 +16,7 @@ inline int grid_for(long long items, int threads, int per_sm = 8) {
 #define GRID_STRIDE(i, n) \
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
-// OP: 0 relu, 1 relu_bwd(a=dy, b=y), 2 add, 3 gelu_bwd(a=dy, b=h)
+// OP: 0 relu, 1 relu_bwd(a=dy, b=y), 2 add, 3 gelu_bwd(a=dy, b=h), 4 gelu
 template <int OP>
 __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                      bf16* __restrict__ out, long long n) {
@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a,
     GRID_STRIDE(i, nv) {
         float x[8], y[8], o[8];
         unpack8(ld8(a + i * 8), x);
-        if (OP != 0) unpack8(ld8(b + i * 8), y);
+        if (OP != 0 && OP != 4) unpack8(ld8(b + i * 8), y);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (OP == 0) o[j] = fmaxf(x[j], 0.f);
             else if (OP == 1) o[j] = (y[j] > 0.f) ? x[j] : 0.f;
             else if (OP == 2) o[j] = x[j] + y[j];
+            else if (OP == 4) o[j] = gelu_erf(x[j]);
             else o[j] = x[j] * gelu_erf_grad(y[j]);
         }
         st8(out + i * 8, pack8(o));
@@ -38,11 +39,12 @@ __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a,
     if (blockIdx.x == 0) {
         for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) {
             const float x = __bfloat162float(a[i]);
-            const float y = (OP != 0) ? __bfloat162float(b[i]) : 0.f;
+            const float y = (OP != 0 && OP != 4) ? __bfloat162float(b[i]) : 0.f;
             float o;
             if (OP == 0) o = fmaxf(x, 0.f);
             else if (OP == 1) o = (y > 0.f) ? x : 0.f;
             else if (OP == 2) o = x + y;
+            else if (OP == 4) o = gelu_erf(x);
             else o = x * gelu_erf_grad(y);
             out[i] = __float2bfloat16(o);
         }
@@ -325,8 +327,8 @@ bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <int OP>
 int launch_binary(const void* a, const void* b, void* out, long long n, void* stream, const char* name) {
-    DFU_CHECK_ARG(a && out && n > 0 && (OP == 0 || b), "%s: bad args", name);
-    DFU_CHECK_ARG(al16(a) && al16(out) && (OP == 0 || al16(b)), "%s: buffers must be 16-byte aligned", name);
+    DFU_CHECK_ARG(a && out && n > 0 && (OP == 0 || OP == 4 || b), "%s: bad args", name);
+    DFU_CHECK_ARG(al16(a) && al16(out) && (OP == 0 || OP == 4 || al16(b)), "%s: buffers must be 16-byte aligned", name);
     binary_kernel<OP><<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
     DFU_CHECK_LAUNCH(name);
     return DFU_OK;
@@ -335,6 +337,7 @@ int launch_binary(const void* a, const void* b, void* out, long long n, void* st
 }  // namespace
 
 extern "C" int dfu_relu(const void* x, void* y, int64_t n, void* stream) { return launch_binary<0>(x, nullptr, y, n, stream, "dfu_relu"); }
+extern "C" int dfu_gelu(const void* x, void* y, int64_t n, void* stream) { return launch_binary<4>(x, nullptr, y, n, stream, "dfu_gelu"); }
 extern "C" int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
     return launch_binary<1>(dy, y, dx, n, stream, "dfu_relu_bwd");
 }

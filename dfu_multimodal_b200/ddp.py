@@ -1,0 +1,130 @@
+"""Data parallelism for the fusion train step (BASELINE config 4; the reference is single-process).
+
+One process per GPU.  Gradients are cast fp32 -> bf16 into ~25 MB flat buckets as autograd produces them
+(post-accumulate-grad hooks, i.e. in reverse layer order) and each full bucket is all-reduced with NCCL on a
+side stream while backward keeps running; FusedAdamW then reads the averaged bf16 buckets directly.  BatchNorm
+statistics stay per rank (the reference has no SyncBN)."""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+BUCKET_BYTES = 25 * 1024 * 1024
+
+
+def _default_cast(src_f32, dst_bf16):
+    """fp32 gradient (dense, any dim order) -> bf16 bucket slice in storage order, with our cast kernel."""
+    ops.cast_f32_bf16(src_f32, 1, src_f32.numel(), src_f32.numel(), out=dst_bf16)
+
+
+class GradBucketer:
+    def __init__(self, params, process_group=None, bucket_bytes=BUCKET_BYTES, cast_fn=None, average=True,
+                 comm_stream=None):
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.cast_fn = cast_fn or _default_cast
+        self.average = average
+        params = [p for p in params if p.requires_grad]
+        self.params = params
+        # reverse registration order ~ the order backward produces gradients (head first, stems last)
+        order = list(reversed(params))
+        self.buckets = []
+        cur, cur_elems = [], 0
+        limit = bucket_bytes // 2
+        for p in order:
+            n = (p.numel() + 7) // 8 * 8          # keep every slice 16-byte aligned
+            if cur and cur_elems + n > limit:
+                self.buckets.append(cur)
+                cur, cur_elems = [], 0
+            cur.append(p)
+            cur_elems += n
+        if cur:
+            self.buckets.append(cur)
+        self.flat = []
+        self.slot = {}
+        for bi, plist in enumerate(self.buckets):
+            total = sum((p.numel() + 7) // 8 * 8 for p in plist)
+            flat = torch.zeros(total, dtype=torch.bfloat16, device=plist[0].device)
+            self.flat.append(flat)
+            off = 0
+            for p in plist:
+                self.slot[p] = (bi, off, p.numel())
+                off += (p.numel() + 7) // 8 * 8
+        self.pending = [0] * len(self.buckets)
+        self.producers = [set() for _ in self.buckets]
+        self.works = []
+        self.is_cuda = params[0].is_cuda
+        self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream() if self.is_cuda else None)
+        self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+
+    # ---------------------------------------------------------------------------------------------------
+    def begin_step(self):
+        self.pending = [len(b) for b in self.buckets]
+        self.producers = [set() for _ in self.buckets]
+        self.works = []
+
+    def _on_grad(self, p):
+        bi, off, n = self.slot[p]
+        g = p.grad
+        if g.stride() != p.stride():
+            g = g.contiguous() if p.is_contiguous() else torch.empty_like(p).copy_(g)
+        self.cast_fn(g, self.flat[bi][off:off + n])
+        if self.is_cuda:
+            # the two model branches may run backward on different streams; remember every producer stream
+            self.producers[bi].add(torch.cuda.current_stream())
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self.world == 1:
+            return
+        flat = self.flat[bi]
+        op = dist.ReduceOp.AVG if (self.average and self.is_cuda) else dist.ReduceOp.SUM
+        if self.is_cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            for s in self.producers[bi]:
+                self.comm_stream.wait_stream(s)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat, op=op, group=self.pg)
+        else:
+            self.works.append(dist.all_reduce(flat, op=op, group=self.pg, async_op=True))
+
+    def finish_step(self):
+        """All buckets reduced and visible to the current stream."""
+        for bi, left in enumerate(self.pending):
+            if left > 0:                 # parameters that received no gradient this step: reduce what is there
+                self.pending[bi] = 0
+                self._launch(bi)
+        if self.is_cuda:
+            if self.world > 1:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            for w in self.works:
+                w.wait()
+            self.works = []
+
+    def grad_source(self, p):
+        """For FusedAdamW.set_grad_source: (bf16 grad slice, is_bf16, scale)."""
+        if p not in self.slot:
+            return None
+        bi, off, n = self.slot[p]
+        scale = 1.0
+        if self.world > 1 and self.average and not self.is_cuda:
+            scale = 1.0 / self.world     # gloo has no AVG
+        return self.flat[bi][off:off + n], True, scale
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+
+def broadcast_parameters(model, src=0, group=None):
+    """Identical replicas at start (rank-0 weights and BN buffers)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+        if hasattr(t, "_dfu_shadow"):
+            t._dfu_shadow = (None, t._dfu_shadow[1])

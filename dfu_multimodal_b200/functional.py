@@ -1,0 +1,448 @@
+"""torch.autograd glue: one Function per fused op of the hot path.  Forward and backward both run only kernels from
+libdfu_b200.so (through ops.py); autograd supplies the graph bookkeeping so `loss.backward()` and
+`optimizer.step()` behave exactly as they do for the reference's nn.Modules
+(notebooks/train_multimodal_fusion.py:374-380)."""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import BF16, F32
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------ bf16 weight shadows
+def shadow(p, rows, cols):
+    """bf16 copy of an fp32 parameter viewed as [rows, cols] in storage order, row stride padded to 8.
+    Cached on the parameter and refreshed when the parameter's version or storage changes."""
+    ldo = _round8(cols)
+    key = (p._version, p.data_ptr(), rows, cols)
+    cached = getattr(p, "_dfu_shadow", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    if cached is not None and cached[1].numel() == rows * ldo and cached[1].device == p.device:
+        buf = cached[1]
+    else:
+        buf = torch.empty((rows, ldo), dtype=BF16, device=p.device)
+    ops.cast_f32_bf16(p.detach(), rows, cols, ldo, out=buf)
+    p._dfu_shadow = (key, buf)
+    return buf
+
+
+def mark_shadow_fresh(p):
+    """Called by the fused optimizer after it wrote the shadow itself."""
+    cached = getattr(p, "_dfu_shadow", None)
+    if cached is not None:
+        k = cached[0]
+        p._dfu_shadow = ((p._version, p.data_ptr(), k[2], k[3]), cached[1])
+
+
+def conv_weight_matrix(weight):
+    """(Cout,Cin,R,S) parameter whose memory is channels_last == row-major [Cout, R*S*Cin]."""
+    Cout, Cin, R, S = weight.shape
+    if not weight.permute(0, 2, 3, 1).is_contiguous():
+        raise RuntimeError("conv weights must be stored channels_last (Cout,R,S,Cin); use DfuConv2d parameters")
+    return shadow(weight, Cout, R * S * Cin)
+
+
+def _as_bf16_2d(g, cols):
+    """Upstream gradient -> dense bf16 [rows, cols]."""
+    g2 = g.reshape(-1, cols)
+    if g2.dtype == F32:
+        g2 = ops.cast_f32_bf16(g2.contiguous()).view(-1, cols)
+    elif not g2.is_contiguous():
+        g2 = g2.contiguous()
+    return g2
+
+
+# ------------------------------------------------------------------------------------------ input adapters
+class ToNHWC(Function):
+    """fp32 NCHW image batch -> bf16 activations (logical NCHW, NHWC memory)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.nchw_f32_to_nhwc_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nhwc_bf16_to_nchw_f32(g)
+
+
+class Patchify(Function):
+    """fp32 (B,3,224,224) -> bf16 patch matrix [B*196, 768] (timm PatchEmbed unfold order c,i,j)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.B = x.shape[0]
+        return ops.patchify_f32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.unpatchify_f32(_as_bf16_2d(g, 768), ctx.B)
+
+
+class CastToF32(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16_f32(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.cast_f32_bf16(g.contiguous()).view(g.shape)
+
+
+class CastToBF16(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_f32_bf16(x.contiguous()).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.cast_bf16_f32(g.contiguous())
+
+
+# ------------------------------------------------------------------------------------------ convolution
+class Conv2dFn(Function):
+    """Implicit-GEMM convolution on NHWC bf16: 1x1/s1 feeds the activation matrix to the GEMM directly, other
+    shapes go through im2col.  Replaces torchvision ResNet's nn.Conv2d (cudnn fwd/dgrad/wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        xn = ops.as_nhwc(x)
+        B, H, W, C = xn.shape
+        Cout, Cin, R, S = weight.shape
+        assert Cin == C, "channel mismatch %d vs %d" % (Cin, C)
+        Ho = (H + 2 * pad - R) // stride + 1
+        Wo = (W + 2 * pad - S) // stride + 1
+        Kc = R * S * C
+        ldc = _round8(Kc)
+        wm = conv_weight_matrix(weight)
+        direct = (R == 1 and S == 1 and stride == 1 and pad == 0 and ldc == Kc)
+        A = xn.reshape(B * H * W, C) if direct else ops.im2col(xn, R, S, stride, pad, Ho, Wo, ldc)
+        y, _ = ops.linear_forward(A, wm)
+        ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct)
+        ctx.save_for_backward(A, weight)
+        return y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        A, weight = ctx.saved_tensors
+        B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct = ctx.geom
+        g = ops.as_nhwc(gy).reshape(B * Ho * Wo, Cout)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.linear_wgrad(g, A)                       # [Cout, ldc] fp32
+            if ldc != Kc:
+                dw = dw[:, :Kc]
+            dw = dw.reshape(Cout, R, S, C).permute(0, 3, 1, 2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wm = conv_weight_matrix(weight)
+            dcol = ops.linear_dgrad(g, wm, ldc)
+            if direct:
+                dx = dcol.view(B, H, W, C)
+            else:
+                dx = ops.col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
+            dx = dx.permute(0, 3, 1, 2)
+        return dx, dw, None, None
+
+
+class BatchNormActFn(Function):
+    """BatchNorm2d (+ residual) (+ ReLU) in two passes over the conv output (stats, apply).  train(): batch
+    statistics + running-stat update (momentum 0.1, unbiased variance) like torch; eval(): running statistics."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, res, running_mean, running_var, nbt, relu, training, eps, momentum):
+        yn = ops.as_nhwc(y)
+        B, H, W, C = yn.shape
+        y2 = yn.reshape(B * H * W, C)
+        res2 = ops.as_nhwc(res).reshape(B * H * W, C) if res is not None else None
+        z, mi = ops.bn_forward(y2, gamma, beta, running_mean, running_var, nbt, res2, relu, training, eps, momentum)
+        ctx.cfg = (B, H, W, C, relu, training, res is not None)
+        ctx.save_for_backward(y2, z if relu else None, mi, gamma)
+        return z.view(B, H, W, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gz):
+        y2, z, mi, gamma = ctx.saved_tensors
+        B, H, W, C, relu, training, has_res = ctx.cfg
+        g = ops.as_nhwc(gz).reshape(B * H * W, C)
+        dy, dres, dg, db = ops.bn_backward(g, z, y2, mi, gamma, relu, training, has_res and ctx.needs_input_grad[3])
+        dy = dy.view(B, H, W, C).permute(0, 3, 1, 2)
+        if dres is not None:
+            dres = dres.view(B, H, W, C).permute(0, 3, 1, 2)
+        return dy, dg, db, dres, None, None, None, None, None, None, None
+
+
+class ReLUFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        xn = ops.as_nhwc(x) if x.dim() == 4 else x.contiguous()
+        y = ops.relu(xn)
+        ctx.save_for_backward(y)
+        ctx.is4 = x.dim() == 4
+        return y.permute(0, 3, 1, 2) if ctx.is4 else y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        gn = ops.as_nhwc(g) if ctx.is4 else _as_bf16_2d(g, y.shape[-1]).view(y.shape)
+        dx = ops.relu_bwd(gn, y)
+        return dx.permute(0, 3, 1, 2) if ctx.is4 else dx
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        if a.dim() == 4:
+            return ops.add(ops.as_nhwc(a), ops.as_nhwc(b)).permute(0, 3, 1, 2)
+        return ops.add(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class GeluFn(Function):
+    """Standalone exact-erf GELU (only used when hooks force the unfused ViT MLP path)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.contiguous()
+        ctx.save_for_backward(xc)
+        return ops.gelu(xc)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(_as_bf16_2d(g, x.shape[-1]).view(x.shape), x)
+
+
+class Fork(Function):
+    """y1 = y2 = x.  Its backward sums the two incoming gradients with our add kernel, so autograd never has to
+    accumulate (which would launch an ATen add) when an activation feeds both a branch and a skip connection."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None:
+            return g2
+        if g2 is None:
+            return g1
+        if g1.dim() == 4:
+            return ops.add(ops.as_nhwc(g1), ops.as_nhwc(g2)).permute(0, 3, 1, 2)
+        c = g1.shape[-1]
+        return ops.add(_as_bf16_2d(g1, c), _as_bf16_2d(g2, c)).view(g1.shape)
+
+
+class MaxPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        xn = ops.as_nhwc(x)
+        y, idx = ops.maxpool(xn, ctx.needs_input_grad[0])
+        ctx.hw = (xn.shape[1], xn.shape[2])
+        ctx.save_for_backward(idx)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return ops.maxpool_bwd(idx, ops.as_nhwc(g), ctx.hw[0], ctx.hw[1]).permute(0, 3, 1, 2)
+
+
+class AvgPoolFn(Function):
+    """AdaptiveAvgPool2d(1) + flatten: (B,C,H,W) -> (B,C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xn = ops.as_nhwc(x)
+        ctx.hw = (xn.shape[1], xn.shape[2])
+        return ops.avgpool(xn)
+
+    @staticmethod
+    def backward(ctx, g):
+        g2 = _as_bf16_2d(g, g.shape[-1])
+        return ops.avgpool_bwd(g2, ctx.hw[0], ctx.hw[1]).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------ linear / ViT
+class LinearFn(Function):
+    """y = act(x W^T + b) (+ res).  act: 0 none, 1 relu, 2 gelu(erf).  Output bf16, or fp32 for logits."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, act, out_fp32):
+        N = weight.shape[0]
+        K = weight.numel() // N          # patch-embed weight is (768,3,16,16): a [768,768] matrix in memory
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        wm = shadow(weight, N, K)
+        res2 = res.reshape(-1, N) if res is not None else None
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]   # (grad mode is off inside forward)
+        y, aux = ops.linear_forward(x2, wm, bias, act, res2, want_aux=(act == 2 and need_grad),
+                                    out_dtype=F32 if out_fp32 else BF16)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.has_res = res is not None
+        ctx.x_shape = x.shape
+        saved_act = aux if act == 2 else (y if act == 1 else None)
+        ctx.save_for_backward(x2, weight, saved_act)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, saved_act = ctx.saved_tensors
+        N = weight.shape[0]
+        K = weight.numel() // N
+        g2 = _as_bf16_2d(gy, N)
+        dres = gy if ctx.has_res else None
+        if ctx.act == 2:
+            g2 = ops.gelu_bwd(g2, saved_act)
+        elif ctx.act == 1:
+            g2 = ops.relu_bwd(g2, saved_act)
+        dw = ops.linear_wgrad(g2, x2, _round8(K)) if ctx.needs_input_grad[1] else None
+        if dw is not None:
+            if dw.shape[1] != K:
+                dw = dw[:, :K]
+            dw = dw.reshape(weight.shape)
+        db = ops.colsum(g2) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_dgrad(g2, shadow(weight, N, K), K).view(ctx.x_shape)
+        return dx, dw, db, dres, None, None
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        y, stats = ops.layernorm(x2, gamma, beta, eps)
+        ctx.save_for_backward(x2, gamma, stats)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, gamma, stats = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(_as_bf16_2d(gy, x2.shape[1]), x2, gamma, stats)
+        return dx.view(gy.shape), dg, db, None
+
+
+class AttentionFn(Function):
+    """softmax(q k^T / 8) v over 197 tokens per (batch, head) on the packed qkv projection (timm Attention)."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, H, scale):
+        q2 = qkv.reshape(B * T, -1)
+        out, P = ops.attention_forward(q2, B, T, H, scale)
+        ctx.cfg = (B, T, H, scale)
+        ctx.save_for_backward(q2, P)
+        return out.view(B, T, H * 64)
+
+    @staticmethod
+    def backward(ctx, g):
+        q2, P = ctx.saved_tensors
+        B, T, H, scale = ctx.cfg
+        dqkv = ops.attention_backward(q2, P, _as_bf16_2d(g, H * 64), B, T, H, scale)
+        return dqkv.view(B, T, -1), None, None, None, None
+
+
+class VitAssembleFn(Function):
+    """cat(cls_token, patch tokens) + pos_embed (timm VisionTransformer._pos_embed)."""
+
+    @staticmethod
+    def forward(ctx, patch_out, cls_token, pos_embed, B):
+        T = pos_embed.shape[1]
+        D = pos_embed.shape[2]
+        ctx.cfg = (B, T, D)
+        return ops.vit_assemble(patch_out, cls_token.detach(), pos_embed.detach(), B, T, D).view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, D = ctx.cfg
+        dpatch, dcls, dpos = ops.vit_assemble_bwd(_as_bf16_2d(g, D), B, T, D)
+        return dpatch, dcls.view(1, 1, D), dpos.view(1, T, D), None
+
+
+class ClsTokenFn(Function):
+    """x[:, 0] of (B,T,D) -> (B,D)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, T, D = x.shape
+        out = torch.empty((B, D), dtype=BF16, device=x.device)
+        ops.copy2d(x, T * D, out, D, B, D)
+        ctx.cfg = (B, T, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, D = ctx.cfg
+        dx = torch.zeros((B, T, D), dtype=BF16, device=g.device)
+        ops.copy2d(_as_bf16_2d(g, D), D, dx, T * D, B, D)
+        return dx
+
+
+class ConcatFn(Function):
+    """cat([a, b], dim=1) for 2-D bf16 feature matrices (train_multimodal_fusion.py:321)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B, Ca = a.shape
+        Cb = b.shape[1]
+        out = torch.empty((B, Ca + Cb), dtype=BF16, device=a.device)
+        ops.copy2d(a.contiguous(), Ca, out, Ca + Cb, B, Ca)
+        ops.copy2d(b.contiguous(), Cb, out, Ca + Cb, B, Cb, dst_off=Ca)
+        ctx.cfg = (B, Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Ca, Cb = ctx.cfg
+        g2 = _as_bf16_2d(g, Ca + Cb)
+        da = torch.empty((B, Ca), dtype=BF16, device=g.device)
+        db = torch.empty((B, Cb), dtype=BF16, device=g.device)
+        ops.copy2d(g2, Ca + Cb, da, Ca, B, Ca)
+        ops.copy2d(g2, Ca + Cb, db, Cb, B, Cb, src_off=Ca)
+        return da, db
+
+
+_DROPOUT_SITE = [0]
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, site):
+        y, mask = ops.dropout(x.contiguous(), p, site)
+        ctx.p = p
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return ops.dropout_bwd(_as_bf16_2d(g, g.shape[-1]).view(g.shape), mask, ctx.p), None, None
+
+
+class CrossEntropyFn(Function):
+    """nn.CrossEntropyLoss(weight=w), mean reduction (train_multimodal_fusion.py:346,376)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight):
+        loss, dlogits = ops.cross_entropy(logits, labels, weight, want_grad=True)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return ops.scale_by_scalar(dlogits, g.contiguous()), None, None
+
+
+def cross_entropy(logits, labels, weight=None):
+    return CrossEntropyFn.apply(logits, labels, weight)

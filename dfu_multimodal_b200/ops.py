@@ -309,13 +309,22 @@ def _binary(fn, name, a, b):
 
 
 def _dense_same_layout(a, b):
-    if a.stride() != b.stride() or a.dtype != b.dtype:
+    sa = [st for st, n in zip(a.stride(), a.shape) if n > 1]
+    sb = [st for st, n in zip(b.stride(), b.shape) if n > 1]
+    if sa != sb or a.shape != b.shape or a.dtype != b.dtype:
         raise RuntimeError("layout mismatch between %s/%s and %s/%s" % (a.stride(), a.dtype, b.stride(), b.dtype))
 
 
 def relu(x):
     out = torch.empty_like(x, memory_format=torch.preserve_format)
     check(_L().dfu_relu(_p(x), _p(out), x.numel(), _st()), "relu")
+    _count()
+    return out
+
+
+def gelu(x):
+    out = torch.empty_like(x, memory_format=torch.preserve_format)
+    check(_L().dfu_gelu(_p(x), _p(out), x.numel(), _st()), "gelu")
     _count()
     return out
 

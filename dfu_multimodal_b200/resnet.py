@@ -1,0 +1,119 @@
+"""ResNet50 (torchvision v1.5 layout: stride on the 3x3 conv, Bottleneck expansion 4) on libdfu_b200 kernels.
+Module/parameter names equal torchvision's so `resnet.*` / `rgb_branch.*` / `backbone.*` checkpoints load
+(SURVEY.md 8b).  Reference constructor: torch.hub.load('pytorch/vision:v0.13.1','resnet50')
+(notebooks/train_multimodal_fusion.py:294)."""
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .nn import (DfuAvgPoolFlatten, DfuBatchNorm2d, DfuConv2d, DfuLinear, DfuMaxPool2d, DfuReLU, convert_head,
+                 has_hooks, to_act)
+
+
+def _conv_bn(x, conv, bn, relu, res=None):
+    y = Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0])
+    return Fn.BatchNormActFn.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var,
+                                   bn.num_batches_tracked, relu, bn.training, bn.eps, bn.momentum)
+
+
+class DfuBottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = DfuConv2d(inplanes, planes, 1)
+        self.bn1 = DfuBatchNorm2d(planes)
+        self.conv2 = DfuConv2d(planes, planes, 3, stride=stride, padding=1)
+        self.bn2 = DfuBatchNorm2d(planes)
+        self.conv3 = DfuConv2d(planes, planes * 4, 1)
+        self.bn3 = DfuBatchNorm2d(planes * 4)
+        self.relu = DfuReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        x = to_act(x)
+        if has_hooks(self):
+            return self._forward_modules(x)
+        needs_fork = torch.is_grad_enabled() and x.requires_grad
+        xm, xs = Fn.Fork.apply(x) if needs_fork else (x, x)
+        out = _conv_bn(xm, self.conv1, self.bn1, True)
+        out = _conv_bn(out, self.conv2, self.bn2, True)
+        identity = xs if self.downsample is None else _conv_bn(xs, self.downsample[0], self.downsample[1], False)
+        return _conv_bn(out, self.conv3, self.bn3, True, res=identity)
+
+    def _forward_modules(self, x):
+        """Unfused path: every submodule is called (and hooked) exactly as in torchvision's Bottleneck.forward."""
+        needs_fork = torch.is_grad_enabled() and x.requires_grad
+        xm, xs = Fn.Fork.apply(x) if needs_fork else (x, x)
+        out = self.relu(self.bn1(self.conv1(xm)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        identity = xs if self.downsample is None else self.downsample(xs)
+        out = Fn.AddFn.apply(out, identity)
+        return self.relu(out)
+
+
+class DfuResNet50(nn.Module):
+    def __init__(self, num_classes=1000):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = DfuConv2d(3, 64, 7, stride=2, padding=3)
+        self.bn1 = DfuBatchNorm2d(64)
+        self.relu = DfuReLU(inplace=True)
+        self.maxpool = DfuMaxPool2d()
+        self.layer1 = self._make_layer(64, 3, 1)
+        self.layer2 = self._make_layer(128, 4, 2)
+        self.layer3 = self._make_layer(256, 6, 2)
+        self.layer4 = self._make_layer(512, 3, 2)
+        self.avgpool = DfuAvgPoolFlatten()
+        self.fc = DfuLinear(2048, num_classes)
+
+    def _make_layer(self, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * 4:
+            downsample = nn.Sequential(DfuConv2d(self.inplanes, planes * 4, 1, stride=stride),
+                                       DfuBatchNorm2d(planes * 4))
+        layers = [DfuBottleneck(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * 4
+        for _ in range(1, blocks):
+            layers.append(DfuBottleneck(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    def __setattr__(self, name, value):
+        # the reference replaces `.fc` with stock torch modules (nn.Identity / Sequential(Dropout, Linear))
+        if name == "fc" and isinstance(value, nn.Module):
+            value = convert_head(value)
+        super().__setattr__(name, value)
+
+    def forward_features(self, x):
+        """(B,3,H,W) fp32 NCHW, or bf16 NHWC-memory activations (e.g. from ops.preprocess_u8_nhwc) -> (B,2048) bf16."""
+        x = to_act(x)
+        if has_hooks(self.conv1, self.bn1, self.relu):
+            x = self.relu(self.bn1(self.conv1(x)))
+        else:
+            x = _conv_bn(x, self.conv1, self.bn1, True)
+        x = self.maxpool(x)
+        x = self.layer1(x)
+        x = self.layer2(x)
+        x = self.layer3(x)
+        x = self.layer4(x)
+        return self.avgpool(x)
+
+    def forward_bf16(self, x):
+        """features -> fc, staying in bf16 (fp32 when fc ends in a Linear producing logits)."""
+        f = self.forward_features(x)
+        if isinstance(self.fc, nn.Identity):
+            return f
+        if isinstance(self.fc, DfuLinear):
+            return self.fc(f, out_fp32=True)
+        return self.fc(f)
+
+    def forward(self, x):
+        """nn.Module contract of torchvision's ResNet: fp32 in, fp32 out."""
+        y = self.forward_bf16(x)
+        return y if y.dtype == torch.float32 else Fn.CastToF32.apply(y)
+
+
+def resnet50(num_classes=1000, **_):
+    return DfuResNet50(num_classes=num_classes)

@@ -108,6 +108,7 @@ int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t B
 int dfu_avgpool(const void* x, void* out, int32_t B, int32_t HW, int32_t C, int64_t ldo, void* stream);
 int dfu_avgpool_bwd(const void* dout, int64_t ldo, void* dx, int32_t B, int32_t HW, int32_t C, void* stream);
 int dfu_relu(const void* x, void* y, int64_t n, void* stream);
+int dfu_gelu(const void* x, void* y, int64_t n, void* stream);
 int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
 int dfu_add(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* dx = dy * gelu'(h) */

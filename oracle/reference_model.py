@@ -1,0 +1,342 @@
+"""ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU fp32 PyTorch restatement of the reference's late-fusion step, used only as the checker by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs.  Nothing under dfu_multimodal_b200/
+imports it.
+
+What it restates (reference = /root/reference, ShreenathKR2000/DFU-Multimodal):
+  * model: MultimodalFusionModel, notebooks/extended_metrics.py:338-367 (canonical key scheme) and the 3-layer
+    training head, notebooks/train_multimodal_fusion.py:305-313;
+  * RGB branch: torchvision.models.resnet50 -- the architecture torch.hub.load('pytorch/vision:v0.13.1','resnet50')
+    returns (train_multimodal_fusion.py:294); imported from the installed torchvision, not restated;
+  * thermal branch: timm `vit_base_patch16_224` (timm>=0.9.2, requirements.txt:19).  timm is NOT in this image and
+    not vendored in the reference, so its published algorithm is restated in OracleViT below in timm's parameter
+    layout.  PINNING: tests/test_oracle.py checks OracleViT against torchvision.models.vit_b_16 (an independent
+    implementation of the same architecture) through a pure key remap, and tests/golden/ holds outputs of the
+    reference's OWN MultimodalFusionModel / GradCAM classes imported from /root/reference with these constructors
+    substituted (oracle/make_golden.py).  The reference itself ships no tests or golden tensors for this path
+    (SURVEY.md section 4), so beyond those two anchors parity is unpinned by the reference;
+  * loss / optimizer: nn.CrossEntropyLoss(weight=w), AdamW(lr 1e-4, wd 1e-4) (train_multimodal_fusion.py:346-347);
+  * preprocessing: ToTensor + Normalize (train_multimodal_fusion.py:184-188, 201-205);
+  * Grad-CAM: restated in oracle_gradcam() from grad_cam_visualization.py:359-429;
+  * TTA vote: test_time_augmentation.py:353-372.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+# --------------------------------------------------------------------------------------------- ViT (timm layout)
+class _Attention(nn.Module):
+    # timm.models.vision_transformer.Attention (0.9.x): qkv -> [3][heads][64], scale 64^-0.5, softmax, proj
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.num_heads = heads
+        self.scale = (dim // heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        attn = (q * self.scale) @ k.transpose(-2, -1)
+        attn = attn.softmax(dim=-1)
+        x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+        return self.proj(x)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class _Block(nn.Module):
+    # timm Block: x + attn(norm1(x)); x + mlp(norm2(x)); LayerNorm eps 1e-6; no drop-path / layer-scale by default
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim, dim * 4)
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, 16, 16)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+class OracleViT(nn.Module):
+    """timm VisionTransformer(vit_base_patch16_224): cls token + pos_embed, 12 pre-norm blocks, final norm,
+    cls pooling, optional head."""
+
+    def __init__(self, num_classes=1000, dim=768, depth=12, heads=12):
+        super().__init__()
+        self.num_classes = num_classes
+        self.patch_embed = _PatchEmbed(dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, 197, dim))
+        self.blocks = nn.Sequential(*[_Block(dim, heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.head = nn.Linear(dim, num_classes) if num_classes > 0 else nn.Identity()
+
+    def forward_features(self, x):
+        x = self.patch_embed(x)
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embed
+        return self.norm(self.blocks(x))
+
+    def forward(self, x):
+        return self.head(self.forward_features(x)[:, 0])
+
+
+def torchvision_vit_to_timm_keys(sd):
+    """Pure key remap torchvision.models.vit_b_16 -> timm layout."""
+    out = {}
+    for k, v in sd.items():
+        k = k.replace("class_token", "cls_token").replace("encoder.pos_embedding", "pos_embed")
+        k = k.replace("conv_proj", "patch_embed.proj").replace("encoder.ln.", "norm.")
+        k = k.replace("encoder.layers.encoder_layer_", "blocks.")
+        k = k.replace(".ln_1.", ".norm1.").replace(".ln_2.", ".norm2.")
+        k = k.replace(".self_attention.in_proj_", ".attn.qkv.").replace(".self_attention.out_proj.", ".attn.proj.")
+        k = k.replace(".mlp.0.", ".mlp.fc1.").replace(".mlp.3.", ".mlp.fc2.")
+        k = k.replace("heads.head.", "head.")
+        out[k] = v
+    return out
+
+
+# --------------------------------------------------------------------------------------------- models
+def oracle_resnet50():
+    import torchvision
+    return torchvision.models.resnet50(weights=None)
+
+
+class OracleMLPFusion(nn.Module):
+    def __init__(self, num_classes=2, dropout=0.7, head_layers=2):
+        super().__init__()
+        if head_layers == 2:
+            self.classifier = nn.Sequential(nn.Linear(2816, 512), nn.ReLU(), nn.Dropout(dropout), nn.Linear(512, num_classes))
+        else:
+            self.classifier = nn.Sequential(nn.Linear(2816, 512), nn.ReLU(), nn.Dropout(dropout), nn.Linear(512, 256),
+                                            nn.ReLU(), nn.Dropout(dropout), nn.Linear(256, num_classes))
+
+    def forward(self, a, b):
+        return self.classifier(torch.cat([a, b], dim=1))
+
+
+class OracleFusion(nn.Module):
+    """extended_metrics.py:353-367 with the constructors substituted (torchvision resnet50, OracleViT)."""
+
+    def __init__(self, num_classes=2, dropout=0.7, head_layers=2):
+        super().__init__()
+        self.resnet = oracle_resnet50()
+        self.resnet.fc = nn.Identity()
+        self.vit = OracleViT(num_classes=0)
+        self.fusion = OracleMLPFusion(num_classes, dropout, head_layers)
+
+    def forward(self, rgb, thermal):
+        return self.fusion(self.resnet(rgb), self.vit(thermal))
+
+
+class OracleRGBOnly(nn.Module):
+    def __init__(self, num_classes=2, drop_rate=0.5):
+        super().__init__()
+        self.resnet = oracle_resnet50()
+        self.resnet.fc = nn.Sequential(nn.Dropout(drop_rate), nn.Linear(2048, num_classes))
+
+    def forward(self, x):
+        return self.resnet(x)
+
+
+class OracleThermalOnly(nn.Module):
+    def __init__(self, num_classes=2, drop_rate=0.5):
+        super().__init__()
+        self.vit = OracleViT(num_classes=num_classes)
+        self.vit.head = nn.Sequential(nn.Dropout(drop_rate), nn.Linear(768, num_classes))
+
+    def forward(self, x):
+        return self.vit(x)
+
+
+def seeded_init_(model, seed=0, calibrate=True):
+    """Deterministic init shared by oracle and CUDA path through one state_dict: conv kaiming-normal
+    fan_out, BN gamma=1 beta=0, linear / ViT weights N(0, 0.02), zero bias, pos_embed / cls N(0, 0.02).
+    BN running stats are then calibrated on one seeded batch (calibrate_bn_) so eval mode is well scaled."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 4 and "patch_embed" not in name:
+                fan_out = p.shape[0] * p.shape[2] * p.shape[3]
+                p.copy_(torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan_out))
+            elif name.endswith("bias"):
+                p.zero_()
+            elif p.dim() == 1:
+                # norm weights: 1, except the last BN of each Bottleneck at 0.25 -- a random residual net with
+                # gamma=1 everywhere amplifies ANY rounding perturbation ~1.25x per block (measured: bf16 rounding
+                # at block boundaries alone gives 17% error at layer4); 0.25 keeps the synthetic network as
+                # well-conditioned as a trained one, so parity tests measure the kernels rather than chaos.
+                p.fill_(0.25 if name.endswith("bn3.weight") else 1.0)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        for name, b in model.named_buffers():
+            if name.endswith("running_mean"):
+                b.copy_(torch.randn(b.shape, generator=g) * 0.05)
+            elif name.endswith("running_var"):
+                b.copy_(1.0 + 0.2 * torch.rand(b.shape, generator=g))
+    if calibrate:
+        calibrate_bn_(model, seed)
+    return model
+
+
+def calibrate_bn_(model, seed=0):
+    """Replaces the BatchNorm running statistics by the batch statistics of one seeded synthetic batch (what a
+    trained checkpoint would hold), so eval-mode activations are well scaled.  Deterministic."""
+    bns = [m for m in model.modules() if isinstance(m, nn.BatchNorm2d)]
+    if not bns:
+        return model
+    rgb_u8, _, _ = synthetic_batch(4, seed + 1000)
+    x = preprocess(rgb_u8, "imagenet")
+    resnet = model.resnet if hasattr(model, "resnet") else model
+    was_training = model.training
+    for m in bns:
+        m.momentum = 1.0
+    resnet.train()
+    with torch.no_grad():
+        r = resnet
+        h = r.maxpool(r.relu(r.bn1(r.conv1(x))))
+        r.layer4(r.layer3(r.layer2(r.layer1(h))))
+    for m in bns:
+        m.momentum = 0.1
+        m.num_batches_tracked.zero_()
+    model.train(was_training)
+    return model
+
+
+def synthetic_batch(B, seed=0):
+    """uint8 HWC image pairs U{0..255} and Bernoulli(146/276) labels."""
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8)
+    thermal = torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8)
+    labels = (torch.rand(B, generator=g) < 146.0 / 276.0).long()
+    return rgb, thermal, labels
+
+
+def preprocess(u8_nhwc, kind):
+    """ToTensor (/255, HWC->CHW) + Normalize; kind 'imagenet' (RGB) or 'half' (thermal 0.5/0.5)."""
+    x = u8_nhwc.float().div(255.0).permute(0, 3, 1, 2)
+    if kind == "imagenet":
+        mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+        std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    else:
+        mean = torch.full((1, 3, 1, 1), 0.5)
+        std = torch.full((1, 3, 1, 1), 0.5)
+    return ((x - mean) / std).contiguous()
+
+
+def class_weights(labels):
+    """train_multimodal_fusion.py:342-346: total / count per class."""
+    n0 = int((labels == 0).sum())
+    n1 = int((labels == 1).sum())
+    tot = max(n0 + n1, 1)
+    return torch.tensor([tot / n0 if n0 > 0 else 0.0, tot / n1 if n1 > 0 else 0.0], dtype=torch.float32)
+
+
+def train_steps(model, batches, weight=None, lr=1e-4, wd=1e-4):
+    """The reference hot loop (train_multimodal_fusion.py:368-388) on CPU; returns the loss per step."""
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
+    crit = nn.CrossEntropyLoss(weight=weight)
+    model.train()
+    losses = []
+    for rgb, thermal, labels in batches:
+        opt.zero_grad()
+        loss = crit(model(rgb, thermal), labels)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return losses
+
+
+# --------------------------------------------------------------------------------------------- Grad-CAM / TTA
+def oracle_gradcam(branch, target_layers, x):
+    """grad_cam_visualization.py:327-429 restated (hooks on every module whose name contains a target string; score =
+    output[0,0]; last matching name; min(C_A, C_G) channels; input-saliency fallback)."""
+    acts, grads = {}, {}
+    handles = []
+
+    def mk(name):
+        def hook(m, i, o):
+            acts[name] = o
+            if isinstance(o, torch.Tensor) and o.requires_grad:
+                o.register_hook(lambda g, n=name: grads.__setitem__(n, g))
+        return hook
+
+    last = None
+    for name, m in branch.named_modules():
+        if any(t in name for t in target_layers):
+            handles.append(m.register_forward_hook(mk(name)))
+            last = name
+    branch.eval()
+    xin = x.clone().detach().requires_grad_(True)
+    with torch.enable_grad():
+        out = branch(xin)
+        branch.zero_grad()
+        out[0, 0].backward()
+    for h in handles:
+        h.remove()
+    A, G = acts[last], grads.get(last)
+    if A.ndim != 4 or G is None or G.ndim != 4:
+        sal = xin.grad.detach().abs().mean(dim=1)[0]
+        if sal.max() > 0:
+            sal = sal / sal.max()
+        return sal.numpy()
+    w = G.mean(dim=(2, 3))
+    n = min(A.shape[1], w.shape[1])
+    cam = (w[0, :n, None, None] * A[0, :n]).sum(0)
+    cam = F.relu(cam)
+    if cam.max() > 0:
+        cam = cam / cam.max()
+    return cam.detach().numpy()
+
+
+def oracle_tta_vote(probs):
+    """probs [N,V] -> (mean prob, majority vote) as test_time_augmentation.py:353-372."""
+    probs = np.asarray(probs, dtype=np.float32)
+    preds = (probs > 0.5).astype(int)
+    return probs.mean(1), (preds.mean(1) > 0.5).astype(int)
+
+
+# --------------------------------------------------------------------------------------------- CPU timing
+def time_cpu_train(B=16, steps=3, warmup=1, threads=None):
+    """Fusion train step on the host cores; returns pairs/s. Bounded: B*(steps+warmup) pairs."""
+    if threads:
+        torch.set_num_threads(threads)
+    model = seeded_init_(OracleFusion(), 0)
+    rgb_u8, th_u8, labels = synthetic_batch(B, 0)
+    rgb, th = preprocess(rgb_u8, "imagenet"), preprocess(th_u8, "half")
+    w = class_weights(labels)
+    batches = [(rgb, th, labels)] * warmup
+    train_steps(model, batches, w)
+    t0 = time.perf_counter()
+    train_steps(model, [(rgb, th, labels)] * steps, w)
+    dt = time.perf_counter() - t0
+    return B * steps / dt
