@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace {
 
@@ -26,7 +27,9 @@ constexpr int STAGES = 4;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_TILE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KB
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;   // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;    // + alignment slack
+constexpr int STG_BYTES = 4096;                             // per epilogue warp: 32 rows x 128 B, SWIZZLE_128B
+constexpr int EPI_BUFS = 1;                                 // staging slabs per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * EPI_BUFS * STG_BYTES + 1024;    // + alignment slack
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
@@ -50,6 +53,8 @@ struct GemmParams {
     float alpha;
     int act;
     int vec_ok;
+    int tma_store;     // epilogue goes through swizzled smem + TMA store / reduce-add
+    int res_vec;
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -120,6 +125,28 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// the staging slab about to be refilled was handed to TMA EPI_BUFS stores ago
+__device__ __forceinline__ void bulk_wait_read_prev() {
+    if (EPI_BUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 // UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -134,6 +161,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ----------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_x,
                    const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES];
@@ -257,6 +285,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
         const int n_chunks = p.block_n / 32;
         int it = 0;
+        int buf = 0;             // staging double buffer (TMA store of slab i overlaps the fill of slab i+1)
         for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
             long long t = w;
             const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
@@ -272,6 +301,128 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const bool row_ok = m < p.M;
             const long long d_off = (long long)z1 * p.sd1 + (long long)z0 * p.sd0 + (long long)m * p.ldd;
             const long long r_off = (long long)z1 * p.sr1 + (long long)z0 * p.sr0 + (long long)m * p.ldr;
+            if (p.tma_store) {
+                // TMEM -> registers -> bias/act/residual -> swizzled smem slab (32 rows x 128 B) -> TMA store.
+                // The two warps of a lane quarter alternate slabs; TMA clips rows >= M and columns >= N.
+                uint8_t* const stg0 = smem + STAGES * STAGE_BYTES + ew * EPI_BUFS * STG_BYTES;
+                uint8_t* stg = stg0 + buf * STG_BYTES;
+                const int slab_cols = p.d_fp32 ? 32 : 64;
+                const int n_slabs = p.block_n / slab_cols;
+                const int chunks = p.d_fp32 ? 1 : 2;
+                const int row0 = m_tile * BLOCK_M + quarter * 32;
+                for (int sl = group; sl < n_slabs; sl += 2) {
+                    const int ncol0 = n_tile * p.block_n + sl * slab_cols;
+                    if (ncol0 >= p.N) break;          // warp-uniform: nothing of this slab is inside the matrix
+                    for (int pass = (p.aux ? 0 : 1); pass < 2; ++pass) {
+                        const bool res_staged = (pass == 1) && p.res && p.res_vec && !p.d_fp32;
+                        if (res_staged) {
+                            // coalesced load of the residual slab into the (swizzled) staging buffer
+                            if (lane == 0) bulk_wait_read_prev();
+                            __syncwarp();
+                            const bf16* rbase = p.res + (long long)z1 * p.sr1 + (long long)z0 * p.sr0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
+                                const int grow = row0 + rr, gcol = ncol0 + cc * 8;
+                                bf16x8 val;
+                                if (grow < p.M && gcol + 8 <= p.N) {
+                                    val = ld8(rbase + (long long)grow * p.ldr + gcol);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) val.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+                                    if (grow < p.M)
+                                        for (int j = 0; j < 8; ++j)
+                                            if (gcol + j < p.N)
+                                                reinterpret_cast<bf16*>(&val)[j] = rbase[(long long)grow * p.ldr + gcol + j];
+                                }
+                                *reinterpret_cast<bf16x8*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4)) = val;
+                            }
+                            __syncwarp();
+                        }
+                        for (int ch = 0; ch < chunks; ++ch) {
+                            uint32_t r[32];
+                            const int col0 = sl * slab_cols + ch * 32;
+                            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N + col0, r);
+                            tmem_ld_wait();
+                            const int nbase = n_tile * p.block_n + col0;
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                            if (p.bias) {
+                                if (nbase + 32 <= p.N) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
+                                        v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
+                                }
+                            }
+                            if (pass == 1) {
+                                if (p.act == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                } else if (p.act == 2) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                                }
+                                if (res_staged) {
+                                    const uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        float rv[8];
+                                        unpack8(*reinterpret_cast<const bf16x8*>(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4)), rv);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
+                                    }
+                                } else if (p.res && row_ok) {
+                                    const bf16* rp = p.res + r_off + nbase;
+                                    if (p.res_vec && nbase + 32 <= p.N) {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            float rv[8];
+                                            unpack8(ld8(rp + q * 8), rv);
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
+                                        }
+                                    } else {
+                                        for (int j = 0; j < 32; ++j)
+                                            if (nbase + j < p.N) v[j] += __bfloat162float(rp[j]);
+                                    }
+                                }
+                            }
+                            if (ch == 0 && !res_staged) {   // this buffer's previous TMA store has read it
+                                if (lane == 0) bulk_wait_read_prev();
+                                __syncwarp();
+                            }
+                            uint8_t* rowp = stg + lane * 128;
+                            if (p.d_fp32) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
+                                        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<bf16x8*>(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4)) = pack8(v + q * 8);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (pass == 0) tma_store_4d(&map_x, stg, ncol0, row0, z0, z1);
+                            else if (p.atomic) tma_reduce_add_4d(&map_d, stg, ncol0, row0, z0, z1);
+                            else tma_store_4d(&map_d, stg, ncol0, row0, z0, z1);
+                            bulk_commit();
+                        }
+                        buf = (buf + 1) % EPI_BUFS;
+                        stg = stg0 + buf * STG_BYTES;
+                    }
+                }
+            } else
             for (int c = group; c < n_chunks; c += 2) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N + c * 32;
@@ -362,6 +513,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (p.tma_store && lane == 0) bulk_wait0();   // all bulk stores of this warp have completed
     }
 
     tc_fence_before();
@@ -447,16 +599,16 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // 4-D bf16 tensor map {inner, rows, z0, z1}; strides in elements.
 int make_map(CUtensorMap* map, const void* base, long long inner, long long rows, long long ld, int nb0, long long s0,
-             int nb1, long long s1, int box_inner, int box_rows) {
+             int nb1, long long s1, int box_inner, int box_rows, int esz = 2) {
     auto enc = get_encode();
     if (!enc) { dfu_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DFU_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
     // strides of dims 1..3 in bytes (multiples of 16); a batch dim of extent 1 only ever sees coordinate 0
-    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb0 > 1 ? s0 : ld) * 2,
-                             (cuuint64_t)(nb1 > 1 ? s1 : ld) * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)(nb0 > 1 ? s0 : ld) * esz,
+                             (cuuint64_t)(nb1 > 1 ? s1 : ld) * esz};
     cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -524,7 +676,13 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     p.M = a->M; p.N = a->N; p.K = a->K; p.nb0 = a->nb0; p.nb1 = a->nb1;
     p.a_mn = a->a_major ? 1 : 0;
     p.b_mn = a->b_major ? 1 : 0;
-    p.block_n = pick_block_n(a->N, p.b_mn);
+    const int esz = a->d_dtype ? 4 : 2;
+    bool d_tma = aligned16(a->D) && ((a->ldd * esz) % 16 == 0) && (a->nb0 == 1 || (a->sd0 * esz) % 16 == 0) &&
+                 (a->nb1 == 1 || (a->sd1 * esz) % 16 == 0);
+    if (a->aux) d_tma = d_tma && aligned16(a->aux) && !a->d_dtype;
+    p.tma_store = d_tma ? 1 : 0;
+    // bf16 TMA-store slabs are 64 columns wide, so block_n must be a multiple of 64 there
+    p.block_n = pick_block_n(a->N, p.b_mn || (d_tma && !a->d_dtype));
     p.m_tiles = dfu_cdiv(a->M, BLOCK_M);
     p.n_tiles = dfu_cdiv(a->N, p.block_n);
     p.num_kb = dfu_cdiv(a->K, BLOCK_K);
@@ -545,11 +703,11 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     p.aux = (bf16*)a->aux; p.bias = a->bias; p.res = (const bf16*)a->res;
     p.ldr = a->ldr; p.sr0 = a->sr0; p.sr1 = a->sr1;
     p.alpha = a->alpha; p.act = a->act;
-    const int esz = a->d_dtype ? 4 : 2;
     bool vec = aligned16(a->D) && ((a->ldd * esz) % 16 == 0) && ((a->sd0 * esz) % 16 == 0) && ((a->sd1 * esz) % 16 == 0);
     if (a->aux) vec = vec && aligned16(a->aux) && (a->ldd % 8 == 0) && (a->sd0 % 8 == 0) && (a->sd1 % 8 == 0);
     if (a->res) vec = vec && aligned16(a->res) && (a->ldr % 8 == 0) && (a->sr0 % 8 == 0) && (a->sr1 % 8 == 0);
     p.vec_ok = vec ? 1 : 0;
+    p.res_vec = (a->res && aligned16(a->res) && (a->ldr % 8 == 0) && (a->sr0 % 8 == 0) && (a->sr1 % 8 == 0)) ? 1 : 0;
 
     CUtensorMap map_a, map_b;
     int rc;
@@ -560,6 +718,18 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     else         rc = make_map(&map_b, a->B, a->N, a->K, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, 64, BLOCK_K);
     if (rc) return rc;
 
+    CUtensorMap map_d, map_x;
+    memset(&map_d, 0, sizeof(map_d));
+    memset(&map_x, 0, sizeof(map_x));
+    if (p.tma_store) {
+        const int slab = a->d_dtype ? 32 : 64;
+        rc = make_map(&map_d, a->D, a->N, a->M, a->ldd, a->nb0, a->sd0, a->nb1, a->sd1, slab, 32, esz);
+        if (rc) return rc;
+        if (a->aux) {
+            rc = make_map(&map_x, a->aux, a->N, a->M, a->ldd, a->nb0, a->sd0, a->nb1, a->sd1, 64, 32, 2);
+            if (rc) return rc;
+        }
+    }
     if (!g_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
@@ -570,7 +740,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         g_attr_set = true;
     }
     const int grid = (int)min((long long)max_ctas, p.total_work);
-    dfu_tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
+    dfu_tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
     return DFU_OK;
 }
