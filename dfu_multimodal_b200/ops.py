@@ -16,6 +16,8 @@ F32 = torch.float32
 _GEMM_IMPL = int(os.environ.get("DFU_GEMM_IMPL", "0"))
 # number of kernels launched through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
+# when set to a list, gemm() appends (start, end) CUDA events for every launch (bench.py roofline measurement)
+GEMM_EVENTS = None
 
 
 def set_gemm_impl(impl):
@@ -72,7 +74,15 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_of
     a.act = act
     a.impl = _GEMM_IMPL if impl is None else impl
     a.max_ctas = max_ctas
-    check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
+    if GEMM_EVENTS is not None:
+        # bench.py's roofline leg: CUDA events around each GEMM launch, on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
+        e1.record()
+        GEMM_EVENTS.append((e0, e1))
+    else:
+        check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
     _count()
     return D
 

@@ -1,0 +1,59 @@
+"""C-ABI surface: the header is the contract; the shared library must export every symbol it declares.
+No compute entry point is called here (there is no GPU in the build container)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from dfu_multimodal_b200 import _lib
+
+
+def test_header_parses_and_names_the_hot_path():
+    protos = _lib.parse_header()
+    for name in ("dfu_gemm", "dfu_im2col_nhwc", "dfu_col2im_nhwc", "dfu_bn_stats", "dfu_bn_apply", "dfu_bn_bwd_apply",
+                 "dfu_layernorm", "dfu_layernorm_bwd", "dfu_softmax_rows", "dfu_cross_entropy", "dfu_adamw",
+                 "dfu_preprocess_u8_nhwc", "dfu_preprocess_u8_patches", "dfu_gradcam", "dfu_tta_vote", "dfu_maxpool3x3s2",
+                 "dfu_avgpool", "dfu_dropout", "dfu_last_error"):
+        assert name in protos, name
+    assert len(protos) >= 45
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build with `python -c 'import __graft_entry__ as g; g.build()'`"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in _lib.parse_header() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_load_sets_signatures_and_version():
+    lib = _lib.load()
+    assert lib.dfu_version() == 100
+    assert lib.dfu_gemm.argtypes == [ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.dfu_last_error.restype == ctypes.c_char_p
+
+
+def test_gemm_args_struct_matches_header_layout():
+    # field order of dfu_gemm_args in include/dfu_b200.h
+    names = [f[0] for f in _lib.GemmArgs._fields_]
+    assert names[:5] == ["M", "N", "K", "nb0", "nb1"]
+    assert names[-4:] == ["alpha", "act", "impl", "max_ctas"]
+    assert ctypes.sizeof(_lib.AdamWTensor) == 48
+
+
+def test_sass_has_blackwell_tensor_and_tma_instructions():
+    exe = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out, "tcgen05.mma missing from SASS"
+    assert "UTMALDG" in out and "UTMASTG" in out, "TMA load/store missing from SASS"
+    assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "HMMA." not in out.replace("UTCHMMA", ""), "legacy mma.sync path present"
+
+
+def test_argument_validation_needs_no_device():
+    lib = _lib.load()
+    assert lib.dfu_gemm(None, None) != 0
+    assert b"null" in lib.dfu_last_error()
+    assert lib.dfu_relu(None, None, 0, None) != 0

@@ -1,0 +1,346 @@
+"""Per-kernel parity on the B200: every entry point of libdfu_b200.so (called through the C ABI via ops.py) against a
+plain PyTorch fp32 reference of the same op on the same seeded inputs.  bf16 outputs are compared with bf16-sized
+tolerances (stated per test); integer/index outputs must be exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_EPS = 2.0 ** -8       # one bf16 ulp relative (8 significand bits incl. hidden one -> 2^-8 spacing)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dfu_multimodal_b200 import ops as o
+    return o
+
+
+def rnd(dev, *shape, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu").manual_seed(seed if seed is not None else sum(shape) + len(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dev).to(torch.bfloat16)
+
+
+def close(got, ref, rel, abs_=0.0):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs().max().item() if got.numel() else 0.0
+    lim = rel * max(1e-30, ref.abs().max().item()) + abs_
+    assert math.isfinite(err) and err <= lim, "max err %.4g > %.4g (ref max %.4g)" % (err, lim, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+GEMM_CASES = [
+    # M, N, K, a_major, b_major, bias, act, res, fp32, acc, aux
+    (128, 64, 64, 0, 0, 0, 0, 0, 0, 0, 0),
+    (300, 200, 96, 0, 0, 1, 0, 0, 0, 0, 0),              # ragged M/N/K tails, bias
+    (1024, 768, 768, 0, 0, 1, 2, 0, 0, 0, 1),            # ViT fc1-like: bias + GELU + pre-activation copy
+    (777, 512, 2816, 0, 0, 1, 1, 1, 0, 0, 0),            # fusion head layer: bias + ReLU (+ residual)
+    (512, 768, 256, 0, 1, 0, 0, 0, 0, 0, 0),             # dgrad form (B MN-major)
+    (768, 3072, 1000, 1, 1, 0, 0, 0, 1, 0, 0),           # wgrad form (A, B MN-major), fp32 store
+    (64, 576, 5000, 1, 1, 0, 0, 0, 1, 1, 0),             # skinny wgrad: split-K + fp32 reduce-add
+    (200, 64, 152, 0, 0, 0, 0, 0, 0, 0, 0),              # stem-like K=152 tail
+    (128, 2, 512, 0, 0, 1, 0, 0, 1, 0, 0),               # 2-logit classifier (SIMT route inside dfu_gemm)
+    (2048, 2304, 768, 0, 0, 1, 0, 0, 0, 0, 0),           # qkv projection
+    (197, 197, 64, 1, 0, 0, 0, 0, 0, 0, 0),
+    (1, 768, 768, 0, 0, 1, 0, 0, 0, 0, 0),               # single row (batch-1 inference)
+    (4, 2816, 4, 1, 1, 0, 0, 0, 1, 1, 0),                # K smaller than one k-block
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "M%d_N%d_K%d_a%d_b%d" % c[:5])
+def test_gemm(ops, dev, case, impl):
+    M, N, K, am, bm, bias, act, res, fp32, acc, aux = case
+    A = rnd(dev, K, M) if am else rnd(dev, M, K)
+    B = rnd(dev, K, N) if bm else rnd(dev, N, K)
+    ref = (A.float().t() if am else A.float()) @ (B.float() if bm else B.float().t())
+    bias_t = torch.randn(N, device=dev) if bias else None
+    if bias:
+        ref = ref + bias_t
+    pre = ref.clone()
+    if act == 1:
+        ref = ref.relu()
+    elif act == 2:
+        ref = F.gelu(ref)
+    res_t = rnd(dev, M, N) if res else None
+    if res:
+        ref = ref + res_t.float()
+    D = torch.full((M, N), 1.0 if acc else float("nan"), dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
+    if acc:
+        ref = ref + 1.0
+    aux_t = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if aux else None
+    ops.gemm(A, B, D, M=M, N=N, K=K, lda=A.stride(0), ldb=B.stride(0), ldd=N, a_major=am, b_major=bm, bias=bias_t,
+             act=act, res=res_t, ldr=N, accumulate=bool(acc), aux=aux_t, impl=impl)
+    torch.cuda.synchronize()
+    # fp32 accumulation of exact bf16 products: only the output rounding (bf16) or summation order (fp32) differs
+    close(D, ref, 2 * BF16_EPS if not fp32 else 1e-5, abs_=1e-3 if not fp32 else 1e-3)
+    if aux:
+        close(aux_t, pre, 2 * BF16_EPS, abs_=1e-3)
+
+
+def test_gemm_alpha_and_padded_leading_dims(ops, dev):
+    M, N, K = 197, 197, 64
+    A, B = rnd(dev, M, 80), rnd(dev, N, 96)                # lda/ldb larger than K
+    D = torch.zeros((M, 200), dtype=torch.bfloat16, device=dev)
+    ops.gemm(A, B, D, M=M, N=N, K=K, lda=80, ldb=96, ldd=200, alpha=0.125)
+    ref = 0.125 * (A[:, :K].float() @ B[:, :K].float().t())
+    close(D[:, :N], ref, 2 * BF16_EPS, 1e-3)
+    assert float(D[:, N:].abs().max()) == 0.0               # pad columns untouched
+
+
+def test_gemm_rejects_bad_arguments(ops, dev):
+    A = rnd(dev, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, A, torch.empty(8, 8, dtype=torch.bfloat16, device=dev), M=8, N=8, K=8, lda=8, ldb=8, ldd=8,
+                 accumulate=True)                            # accumulate needs fp32 output
+
+
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B", [1, 3])
+def test_attention_forward_backward(ops, dev, B):
+    T, H = 197, 12
+    qkv = rnd(dev, B * T, 3 * H * 64, scale=0.5)
+    out, P = ops.attention_forward(qkv, B, T, H, 0.125)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o = ((q @ k.transpose(-1, -2) * 0.125).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
+    close(out, o, 1e-2, 1e-3)
+    do = rnd(dev, B * T, H * 64)
+    o.backward(do.float())
+    dqkv = ops.attention_backward(qkv, P, do, B, T, H, 0.125)
+    dref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * T, 3 * H * 64)
+    close(dqkv, dref, 2e-2, 1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- layout
+def test_preprocess_u8(ops, dev):
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8).to(dev)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+    ref = ((img.float() / 255 - mean) / std).permute(0, 3, 1, 2)
+    close(ops.preprocess_u8_nhwc(img, "imagenet"), ref, BF16_EPS)
+    refh = ((img.float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)
+    patches = refh.reshape(3, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(3 * 196, 768)
+    close(ops.preprocess_u8_patches(img, "half"), patches, BF16_EPS)
+    odd = img[:1, :5, :7].contiguous()                      # pixel count not a multiple of 16: tail path
+    close(ops.preprocess_u8_nhwc(odd, "half"), ((odd.float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2), BF16_EPS)
+
+
+def test_layout_conversions(ops, dev):
+    x = torch.randn(2, 70, 9, 11, device=dev)
+    y = ops.nchw_f32_to_nhwc_bf16(x)
+    assert y.shape == x.shape and y.permute(0, 2, 3, 1).is_contiguous()
+    close(y, x, BF16_EPS)
+    assert torch.equal(ops.nhwc_bf16_to_nchw_f32(y), y.float())
+    img = torch.randn(2, 3, 224, 224, device=dev)
+    ref = img.reshape(2, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(2 * 196, 768)
+    close(ops.patchify_f32(img), ref, BF16_EPS)
+    dp = rnd(dev, 2 * 196, 768)
+    back = dp.float().view(2, 14, 14, 3, 16, 16).permute(0, 3, 1, 4, 2, 5).reshape(2, 3, 224, 224)
+    assert torch.equal(ops.unpatchify_f32(dp, 2), back)
+
+
+@pytest.mark.parametrize("C,R,stride,pad,H", [(64, 3, 1, 1, 14), (64, 3, 2, 1, 14), (3, 7, 2, 3, 32), (128, 1, 2, 0, 8),
+                                              (256, 3, 1, 1, 7)])
+def test_im2col_col2im(ops, dev, C, R, stride, pad, H):
+    x = rnd(dev, 2, C, H, H)
+    xn = ops.as_nhwc(ops.nchw_f32_to_nhwc_bf16(x.float()))
+    Ho = (H + 2 * pad - R) // stride + 1
+    Kc = R * R * C
+    ldc = (Kc + 7) // 8 * 8
+    col = ops.im2col(xn, R, R, stride, pad, Ho, Ho, ldc)
+    unf = F.unfold(x.float(), (R, R), padding=pad, stride=stride)
+    ref = unf.view(2, C, R * R, Ho * Ho).permute(0, 3, 2, 1).reshape(2 * Ho * Ho, Kc)
+    assert torch.equal(col[:, :Kc].float(), ref)            # pure data movement: exact
+    if ldc > Kc:
+        assert float(col[:, Kc:].abs().max()) == 0.0
+    dcol = rnd(dev, 2 * Ho * Ho, ldc)
+    dx = ops.col2im(dcol, 2, H, H, C, R, R, stride, pad, Ho, Ho, ldc)
+    dunf = dcol[:, :Kc].float().view(2, Ho * Ho, R * R, C).permute(0, 3, 2, 1).reshape(2, C * R * R, Ho * Ho)
+    close(dx.permute(0, 3, 1, 2), F.fold(dunf, (H, H), (R, R), padding=pad, stride=stride), 2 * BF16_EPS, 1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- BatchNorm / LayerNorm
+@pytest.mark.parametrize("C,M", [(64, 5000), (256, 777), (2048, 98), (512, 1)])
+def test_batchnorm_train_eval_backward(ops, dev, C, M):
+    y = rnd(dev, M, C) * 2 + 0.5
+    gamma = torch.rand(C, device=dev) + 0.5
+    beta = torch.randn(C, device=dev)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    nbt = torch.zeros((), dtype=torch.int64, device=dev)
+    res = rnd(dev, M, C)
+    if M > 1:
+        z, mi = ops.bn_forward(y, gamma, beta, rm, rv, nbt, res, True, True, 1e-5, 0.1)
+        yf, g, b, rf = y.float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), res.float().requires_grad_(True)
+        rm2, rv2 = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        pre = F.batch_norm(yf, rm2, rv2, g, b, True, 0.1, 1e-5) + rf
+        close(z, pre.relu(), 2 * BF16_EPS, 2e-3)
+        close(rm, rm2, 1e-4, 1e-6)
+        close(rv, rv2, 1e-4, 1e-6)
+        assert int(nbt.item()) == 1
+        dz = rnd(dev, M, C)
+        (pre * (z.float() > 0)).backward(dz.float())       # ReLU mask of OUR output: avoids tie noise at 0
+        dy, dres, dg, db = ops.bn_backward(dz, z, y, mi, gamma, True, True, True)
+        close(dy, yf.grad, 3 * BF16_EPS, 2e-3)
+        close(dres, rf.grad, BF16_EPS)
+        close(dg, g.grad, 1e-3, 1e-3)
+        close(db, b.grad, 1e-3, 1e-3)
+    rm.normal_(0, 0.1)
+    rv.uniform_(0.5, 1.5)
+    z2, _ = ops.bn_forward(y, gamma, beta, rm, rv, nbt, None, False, False, 1e-5, 0.1)
+    close(z2, F.batch_norm(y.float(), rm, rv, gamma, beta, False, 0.1, 1e-5), 2 * BF16_EPS, 2e-3)
+
+
+@pytest.mark.parametrize("rows,D", [(1000, 768), (3, 768), (197, 1024), (64, 256)])
+def test_layernorm(ops, dev, rows, D):
+    x = rnd(dev, rows, D) * 1.5 + 0.3
+    g, b = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev)
+    y, stats = ops.layernorm(x, g, b, 1e-6)
+    xf, gf, bf = x.float().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.layer_norm(xf, (D,), gf, bf, 1e-6)
+    close(y, yr, 2 * BF16_EPS, 2e-3)
+    dy = rnd(dev, rows, D)
+    yr.backward(dy.float())
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, stats)
+    close(dx, xf.grad, 3 * BF16_EPS, 2e-3)
+    close(dg, gf.grad, 1e-3, 1e-3)
+    close(db, bf.grad, 1e-3, 1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- pooling / pointwise
+def test_maxpool_avgpool(ops, dev):
+    x = rnd(dev, 2, 64, 20, 20)
+    x[0, :, :4, :4] = 0                                      # ties (all-equal windows, as after ReLU)
+    xn = ops.as_nhwc(ops.nchw_f32_to_nhwc_bf16(x.float()))
+    y, idx = ops.maxpool(xn, True)
+    xf = x.float().requires_grad_(True)
+    yr = F.max_pool2d(xf, 3, 2, 1)
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), yr)
+    dy = rnd(dev, 2, 10, 10, 64)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    close(ops.maxpool_bwd(idx, dy, 20, 20).permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 1e-3)   # same tie-break as ATen
+    x = rnd(dev, 4, 7, 7, 2048)
+    close(ops.avgpool(x), x.float().mean((1, 2)), 2 * BF16_EPS, 1e-3)
+    d = rnd(dev, 4, 2048)
+    close(ops.avgpool_bwd(d, 7, 7), (d.float() / 49)[:, None, None, :].expand(4, 7, 7, 2048), 2 * BF16_EPS)
+
+
+@pytest.mark.parametrize("n", [8, 1001, 65536 + 3])
+def test_pointwise(ops, dev, n):
+    a, b = rnd(dev, n), rnd(dev, n, seed=n + 1)
+    assert torch.equal(ops.relu(a).float(), a.float().relu())
+    assert torch.equal(ops.relu_bwd(a, b).float(), a.float() * (b.float() > 0))
+    close(ops.add(a, b), a.float() + b.float(), BF16_EPS)
+    close(ops.gelu(a), F.gelu(a.float()), 2 * BF16_EPS, 1e-3)
+    hf = b.float().requires_grad_(True)
+    F.gelu(hf).backward(a.float())
+    close(ops.gelu_bwd(a, b), hf.grad, 2 * BF16_EPS, 1e-3)
+
+
+def test_colsum_cast_copy(ops, dev):
+    x = rnd(dev, 3000, 768)
+    close(ops.colsum(x), x.float().sum(0), 1e-5, 1e-3)
+    x2 = rnd(dev, 128, 2)
+    close(ops.colsum(x2), x2.float().sum(0), 1e-5, 1e-4)
+    w = torch.randn(64, 147, device=dev)
+    c = ops.cast_f32_bf16(w, 64, 147, 152).view(64, 152)
+    assert torch.equal(c[:, :147], w.to(torch.bfloat16)) and float(c[:, 147:].abs().max()) == 0.0
+    w = torch.randn(1000, 77, device=dev)
+    assert torch.equal(ops.cast_f32_bf16(w).view(1000, 77), w.to(torch.bfloat16))
+    assert torch.equal(ops.cast_bf16_f32(x), x.float())
+    dst = torch.zeros(4, 2816, dtype=torch.bfloat16, device=dev)
+    src = rnd(dev, 4, 768)
+    ops.copy2d(src, 768, dst, 2816, 4, 768, dst_off=2048)
+    assert torch.equal(dst[:, 2048:], src) and float(dst[:, :2048].abs().max()) == 0.0
+
+
+def test_dropout(ops, dev):
+    x = rnd(dev, 200000)
+    y, m = ops.dropout(x, 0.7, 1)
+    keep = m.float().mean().item()
+    assert abs(keep - 0.3) < 0.01
+    assert torch.equal(y.float(), (x.float() * m.float() / 0.3).to(torch.bfloat16).float())
+    close(ops.dropout_bwd(x, m, 0.7), x.float() * m.float() / 0.3, BF16_EPS)
+    y2, m2 = ops.dropout(x, 0.7, 2)
+    assert not torch.equal(m, m2)                            # call sites draw different masks
+    ops.DROPOUT.tick(dev)
+    _, m3 = ops.dropout(x, 0.7, 1)
+    assert not torch.equal(m, m3)                            # and so do successive steps
+
+
+def test_vit_assemble(ops, dev):
+    B, T, D = 3, 197, 768
+    po, cls, pos = rnd(dev, B * 196, D), torch.randn(D, device=dev), torch.randn(T * D, device=dev)
+    tok = ops.vit_assemble(po, cls, pos, B, T, D)
+    ref = torch.cat([cls.view(1, 1, D).expand(B, 1, D), po.float().view(B, 196, D)], 1) + pos.view(1, T, D)
+    close(tok.view(B, T, D), ref, 2 * BF16_EPS)
+    dt = rnd(dev, B * T, D)
+    dpa, dcls, dpos = ops.vit_assemble_bwd(dt, B, T, D)
+    assert torch.equal(dpa.view(B, 196, D), dt.view(B, T, D)[:, 1:])
+    close(dcls, dt.float().view(B, T, D)[:, 0].sum(0), 1e-6, 1e-5)
+    close(dpos.view(T, D), dt.float().view(B, T, D).sum(0), 1e-6, 1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- loss / metrics / cam
+@pytest.mark.parametrize("B", [1, 6, 128, 1000])
+def test_cross_entropy_and_predict(ops, dev, B):
+    g = torch.Generator().manual_seed(B)
+    logits = (torch.randn(B, 2, generator=g) * 3).to(dev)
+    labels = torch.randint(0, 2, (B,), generator=g).to(dev)
+    w = torch.tensor([2.1, 1.9], device=dev)
+    for weight in (w, None):
+        loss, dl = ops.cross_entropy(logits, labels, weight)
+        lf = logits.clone().requires_grad_(True)
+        lr = F.cross_entropy(lf, labels, weight=weight)
+        lr.backward()
+        close(loss.view(1), lr.view(1), 1e-5, 1e-6)
+        close(dl, lf.grad, 1e-4, 1e-7)
+    p1, pred = ops.predict(logits)
+    close(p1, logits.softmax(1)[:, 1], 1e-5, 1e-6)
+    assert torch.equal(pred, logits.argmax(1))
+
+
+def test_gradcam_saliency_tta(ops, dev):
+    A, G = rnd(dev, 49, 2048), rnd(dev, 49, 512)
+    cam = ops.gradcam_reduce(A, G, 512)
+    ref = (A.float()[:, :512] * G.float().mean(0)).sum(1).relu()
+    ref = ref / ref.max()
+    close(cam, ref, 1e-4, 1e-5)
+    zero = ops.gradcam_reduce(A, torch.zeros_like(G), 512)
+    assert float(zero.abs().max()) == 0.0                     # max == 0 -> no normalisation (reference :426)
+    d = torch.randn(3, 224, 224, device=dev)
+    sal = d.abs().mean(0)
+    close(ops.saliency(d), sal / sal.max(), 1e-5, 1e-6)
+    probs = torch.rand(276, 8, device=dev)
+    probs[0] = torch.tensor([0.6, 0.6, 0.6, 0.6, 0.4, 0.4, 0.4, 0.4])      # tie -> class 0
+    mp, pr = ops.tta_vote(probs)
+    close(mp, probs.mean(1), 1e-6, 1e-7)
+    assert torch.equal(pr, ((probs > 0.5).float().mean(1) > 0.5).long()) and int(pr[0]) == 0
+
+
+def test_fused_adamw_matches_torch_adamw(dev):
+    from dfu_multimodal_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(64, 3, 7, 7), (768,), (2304, 768), (1, 197, 768), (5,), (70000,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    a = FusedAdamW(ps, lr=1e-3, weight_decay=1e-2)
+    b = torch.optim.AdamW(qs, lr=1e-3, weight_decay=1e-2)
+    for step in range(3):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = g.clone()
+            q.grad = g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        close(p, q, 1e-5, 1e-6)

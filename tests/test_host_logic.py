@@ -1,0 +1,151 @@
+"""Host-side logic that needs no GPU: module tree / state_dict compatibility, checkpoint key remaps for the four
+reference schemes, the timm / torch.hub drop-in, head conversion, hook detection, and the
+fail-loudly contract (no CPU fallback)."""
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+import dfu_multimodal_b200 as D
+from dfu_multimodal_b200 import checkpoint, dropin
+from dfu_multimodal_b200.nn import DfuDropout, DfuHead, DfuLinear, has_hooks
+from oracle import reference_model as R
+
+
+def test_fusion_state_dict_equals_oracle_layout():
+    ours = D.MultimodalFusionModel().state_dict()
+    ref = R.OracleFusion().state_dict()
+    assert list(ours.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(ours[k].shape) == tuple(ref[k].shape), k
+    m = D.MultimodalFusionModel()
+    assert sum(p.numel() for p in m.parameters()) == 110_750_018
+
+
+def test_load_oracle_weights_roundtrip_keeps_channels_last_conv_storage():
+    oracle = R.seeded_init_(R.OracleFusion(), 0, calibrate=False)
+    m = D.MultimodalFusionModel()
+    res = m.load_state_dict(oracle.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    w = m.resnet.layer1[0].conv2.weight
+    assert w.permute(0, 2, 3, 1).is_contiguous()           # storage is [Cout, R, S, Cin]
+    assert torch.equal(w, oracle.resnet.layer1[0].conv2.weight)
+    back = m.state_dict()
+    assert all(torch.equal(back[k], v) for k, v in oracle.state_dict().items())
+
+
+def test_single_modality_models_use_reference_key_names():
+    rgb = D.RGBOnlyModel().state_dict()
+    assert "resnet.fc.1.weight" in rgb and rgb["resnet.fc.1.weight"].shape == (2, 2048)
+    th = D.ThermalOnlyModel().state_dict()
+    assert "vit.head.1.weight" in th and th["vit.head.1.weight"].shape == (2, 768)
+    assert list(rgb.keys()) == list(R.OracleRGBOnly().state_dict().keys())
+    assert list(th.keys()) == list(R.OracleThermalOnly().state_dict().keys())
+
+
+def _canon():
+    return R.seeded_init_(R.OracleFusion(), 3, calibrate=False).state_dict()
+
+
+def test_remap_train_scheme_with_three_layer_head():
+    sd = R.seeded_init_(R.OracleFusion(head_layers=3), 3, calibrate=False).state_dict()
+    train = {}
+    for k, v in sd.items():                                # what train_multimodal_fusion.py:294-313 writes
+        k = k.replace("resnet.", "rgb_branch.", 1) if k.startswith("resnet.") else k
+        k = k.replace("vit.", "thermal_branch.", 1) if k.startswith("vit.") else k
+        k = k.replace("fusion.classifier.", "fusion.")
+        train[k] = v
+    assert checkpoint.detect_scheme(train) == "train"
+    model = checkpoint.build_fusion_from_checkpoint({"model_state_dict": train, "epoch": 4})
+    assert isinstance(model.fusion.classifier[6], DfuLinear)
+    assert torch.equal(model.state_dict()["fusion.classifier.6.weight"], sd["fusion.classifier.6.weight"])
+    assert torch.equal(model.state_dict()["resnet.layer3.2.conv2.weight"], sd["resnet.layer3.2.conv2.weight"])
+
+
+def test_remap_ablation_legacy_and_eval_schemes():
+    sd = _canon()
+    abl = {k.replace("resnet.", "rgb_branch.", 1).replace("vit.", "thermal_branch.", 1).replace("fusion.classifier.", "fusion."): v
+           for k, v in sd.items()}
+    assert checkpoint.detect_scheme(abl) == "ablation"
+    legacy = {("backbone." + k[7:] if k.startswith("resnet.") else "vit_backbone." + k[4:] if k.startswith("vit.") else k): v
+              for k, v in sd.items()}
+    for variant in (abl, legacy, sd):
+        m = D.MultimodalFusionModel()
+        res = checkpoint.load_into(m, {"model_state_dict": variant}, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert torch.equal(m.state_dict()["vit.blocks.7.attn.qkv.weight"], sd["vit.blocks.7.attn.qkv.weight"])
+
+
+def test_remap_single_modality_backbone_prefix():
+    rgb = R.OracleRGBOnly().state_dict()
+    train = {k.replace("resnet.", "backbone.", 1): v for k, v in rgb.items()}       # train_rgb_only.py:206-214
+    m = D.RGBOnlyModel()
+    assert not checkpoint.load_into(m, train, target="rgb").missing_keys
+    th = R.OracleThermalOnly().state_dict()
+    train = {k.replace("vit.", "backbone.", 1): v for k, v in th.items()}           # train_thermal_only.py:194-202
+    m = D.ThermalOnlyModel()
+    assert not checkpoint.load_into(m, train, target="thermal").missing_keys
+
+
+def test_strict_load_reports_scheme_mismatch_instead_of_silently_skipping():
+    m = D.MultimodalFusionModel()
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"rgb_branch.conv1.weight": torch.zeros(64, 3, 7, 7)}, strict=True)
+
+
+def test_dropin_timm_shim_and_hub_interceptor():
+    dropin.install(force_timm_shim=True)
+    try:
+        import timm
+        vit = timm.create_model("vit_base_patch16_224", pretrained=False, num_classes=0)
+        assert isinstance(vit, D.DfuVisionTransformer) and isinstance(vit.head, nn.Identity)
+        vit2 = timm.create_model("vit_base_patch16_224", pretrained=False, num_classes=2)
+        assert vit2.head.in_features == 768
+        vit2.head = nn.Sequential(nn.Dropout(p=0.5), nn.Linear(768, 2))             # train_thermal_only.py:199-202
+        assert isinstance(vit2.head, DfuHead) and isinstance(vit2.head[1], DfuLinear) and isinstance(vit2.head[0], DfuDropout)
+        assert "head.1.weight" in vit2.state_dict()
+        with pytest.raises(RuntimeError):
+            timm.create_model("resnet18")
+        rn = torch.hub.load("pytorch/vision:v0.13.1", "resnet50", pretrained=False)
+        assert isinstance(rn, D.DfuResNet50) and rn.fc.in_features == 2048
+        rn.fc = nn.Identity()                                                        # train_multimodal_fusion.py:296
+        assert isinstance(rn.fc, nn.Identity)
+        rn.fc = nn.Sequential(nn.Dropout(0.5), nn.Linear(2048, 2))                   # train_rgb_only.py:211-214
+        assert "fc.1.bias" in rn.state_dict()
+        names = [n for n, _ in rn.named_modules()]
+        assert "layer4.2.relu" in names and "layer4.0.downsample.1" in names
+        assert any(n.startswith("blocks.11") for n, _ in vit.named_modules())
+    finally:
+        dropin.uninstall()
+    assert "timm" not in sys.modules or not getattr(sys.modules["timm"], "__dfu_shim__", False)
+
+
+def test_has_hooks_switches_off_fused_paths():
+    m = D.DfuResNet50()
+    blk = m.layer4[2]
+    assert not has_hooks(blk)
+    h = blk.relu.register_forward_hook(lambda mod, i, o: None)
+    assert has_hooks(blk)
+    h.remove()
+    assert not has_hooks(blk)
+
+
+def test_no_cpu_fallback_product_path_fails_loudly():
+    m = D.MultimodalFusionModel()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 224, 224), torch.zeros(1, 3, 224, 224))
+    from dfu_multimodal_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.predict(torch.zeros(2, 2))
+    import inspect
+    import dfu_multimodal_b200.ops as ops_mod
+    src = inspect.getsource(ops_mod) + inspect.getsource(D.fusion) + inspect.getsource(D.resnet) + inspect.getsource(D.vit)
+    assert "oracle" not in src, "product code must not import the oracle"
+
+
+def test_head_builder_variants():
+    from dfu_multimodal_b200.fusion import make_head
+    h2, h3 = make_head(2816, 2, 0.7, 2), make_head(2816, 2, 0.5, 3)
+    assert [k for k in h2.state_dict()] == ["0.weight", "0.bias", "3.weight", "3.bias"]
+    assert [k for k in h3.state_dict()] == ["0.weight", "0.bias", "3.weight", "3.bias", "6.weight", "6.bias"]
