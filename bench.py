@@ -243,7 +243,7 @@ def main():
         eager(*devb[1])
         torch.cuda.synchronize()
         evs, ops.GEMM_EVENTS = ops.GEMM_EVENTS, None
-        gemm_ms = sum(a.elapsed_time(b) for a, b in evs)
+        gemm_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
         n_gemm = len(evs)
         flops_step = TRAIN_GFLOP_PER_PAIR * 1e9 * B
         achieved = flops_step / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None

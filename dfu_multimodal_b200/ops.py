@@ -80,7 +80,9 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_of
         e0.record()
         check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
         e1.record()
-        GEMM_EVENTS.append((e0, e1))
+        GEMM_EVENTS.append((e0, e1, (M, N, K, nb0 * nb1, a_major, b_major, "f32" if D.dtype == F32 else "bf16",
+                                     int(bool(accumulate)), int(bias is not None), act, int(res is not None),
+                                     int(aux is not None))))
     else:
         check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
     _count()
