@@ -205,6 +205,56 @@ __global__ void __launch_bounds__(256) im2col_scalar_kernel(const bf16* __restri
         col[t] = __float2bfloat16(val);
     }
 }
+
+// Stem path (C = 3, e.g. the 7x7/s2 first convolution): one block per (image, output row).  The R input rows the
+// output row touches are staged in shared memory with 128-bit loads, then every thread assembles 8 consecutive
+// columns of one col row (k = (r*S + s)*3 + c, i.e. S*3 contiguous input elements per filter row) and writes them
+// with one 128-bit store; consecutive threads write consecutive 16-byte chunks, so stores are fully coalesced.
+__global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W,
+                                                        int R, int S, int stride, int pad, int Ho, int Wo,
+                                                        int ldc) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [R][W*3]
+    const int ho = blockIdx.x % Ho;
+    const int b = blockIdx.x / Ho;
+    const int rowlen = W * 3;
+    const int vec_per_row = rowlen >> 3;
+    for (int t = threadIdx.x; t < R * vec_per_row; t += blockDim.x) {
+        const int r = t / vec_per_row, v = t - r * vec_per_row;
+        const int h = ho * stride - pad + r;
+        bf16x8 val;
+        if (h >= 0 && h < H) {
+            val = ld8(x + ((long long)b * H + h) * rowlen + v * 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) val.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+        }
+        *reinterpret_cast<bf16x8*>(rows + r * rowlen + v * 8) = val;
+    }
+    __syncthreads();
+    const int chunks = ldc >> 3;
+    const int Kc = R * S * 3;
+    const int seg = S * 3;
+    bf16* out = col + ((long long)b * Ho + ho) * Wo * ldc;
+    const bf16 zero = __float2bfloat16(0.f);
+    for (int t = threadIdx.x; t < Wo * chunks; t += blockDim.x) {
+        const int wo = t / chunks, ch = t - wo * chunks;
+        const int w0 = (wo * stride - pad) * 3;
+        alignas(16) bf16 e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = ch * 8 + i;
+            bf16 v = zero;
+            if (k < Kc) {
+                const int r = k / seg, j = k - r * seg;
+                const int we = w0 + j;
+                if (we >= 0 && we < rowlen) v = rows[r * rowlen + we];
+            }
+            e[i] = v;
+        }
+        *reinterpret_cast<bf16x8*>(out + (long long)t * 8) = *reinterpret_cast<const bf16x8*>(e);
+    }
+}
 // Zero the pad columns [Kc, ldc) of the vector path when ldc > Kc.
 __global__ void __launch_bounds__(256) zero_pad_cols_kernel(bf16* __restrict__ col, long long rows, int Kc, long long ldc) {
     const int padw = (int)(ldc - Kc);
@@ -358,6 +408,11 @@ extern "C" int dfu_im2col_nhwc(const void* x, void* col, int32_t B, int32_t H, i
             zero_pad_cols_kernel<<<grid_for(rows * (ldc - R * S * C), 256), 256, 0, st>>>((bf16*)col, rows, R * S * C, ldc);
             DFU_CHECK_LAUNCH("zero_pad_cols");
         }
+    } else if (C == 3 && (W * 3) % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0 &&
+               (size_t)R * W * 3 * sizeof(bf16) <= 48 * 1024) {
+        im2col_c3_kernel<<<B * Ho, 256, (size_t)R * W * 3 * sizeof(bf16), st>>>((const bf16*)x, (bf16*)col, H, W, R, S, stride,
+                                                                            pad, Ho, Wo, (int)ldc);
+        DFU_CHECK_LAUNCH("im2col_c3");
     } else {
         im2col_scalar_kernel<<<grid_for(rows * ldc, 256, 16), 256, 0, st>>>((const bf16*)x, (bf16*)col, B, H, W, C, R, S,
                                                                             stride, pad, Ho, Wo, ldc);

@@ -13,6 +13,7 @@ inline int grid_cap(long long blocks, int per_sm) {
 }
 
 // ------------------------------------------------------------------------------------------ BatchNorm
+constexpr int BN_UNROLL = 4;
 // Thread layout: 256 threads = (256/cvec) row lanes x cvec channel vectors (8 channels each).
 // MODE 0: sums of y and y^2.  MODE 1 (backward): sums of dpre and dpre*xhat.
 template <int MODE>
@@ -35,27 +36,45 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
             invstd[i] = mean_invstd[C + cv * 8 + i];
         }
     }
-    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
-        const long long off = r * C + cv * 8;
-        float f[8];
-        if (MODE == 0) {
-            unpack8(ld8(a + off), f);
+    // BN_UNROLL rows per thread per trip: all 128-bit loads are issued before any is consumed (memory-level parallelism)
+    const long long rstride = (long long)gridDim.x * rows_per_iter;
+    for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
+        bf16x8 va[BN_UNROLL], vy[BN_UNROLL], vz[BN_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
-        } else {
-            float zz[8], yy[8];
-            unpack8(ld8(a + off), f);     // dz
-            unpack8(ld8(y + off), yy);
-            if (relu) {
-                unpack8(ld8(z + off), zz);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) f[i] = 0.f;
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r < M) {
+                const long long off = r * C + cv * 8;
+                va[u] = ld8(a + off);
+                if (MODE == 1) {
+                    vy[u] = ld8(y + off);
+                    if (relu) vz[u] = ld8(z + off);
+                }
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xh = (yy[i] - mean[i]) * invstd[i];
-                s1[i] += f[i];
-                s2[i] += f[i] * xh;
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r >= M) break;
+            float f[8];
+            unpack8(va[u], f);
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
+            } else {
+                float zz[8], yy[8];
+                unpack8(vy[u], yy);
+                if (relu) {
+                    unpack8(vz[u], zz);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) f[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float xh = (yy[i] - mean[i]) * invstd[i];
+                    s1[i] += f[i];
+                    s2[i] += f[i] * xh;
+                }
             }
         }
     }
@@ -114,23 +133,38 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
         sc[i] = gamma[c] * mean_invstd[C + c];
         sh[i] = beta[c] - mean_invstd[c] * sc[i];
     }
-    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
-        const long long off = r * C + cv * 8;
-        float f[8];
-        unpack8(ld8(y + off), f);
+    const long long rstride = (long long)gridDim.x * rows_per_iter;
+    for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
+        bf16x8 vy[BN_UNROLL], vr[BN_UNROLL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
-        if (res) {
-            float rr[8];
-            unpack8(ld8(res + off), rr);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += rr[i];
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r < M) {
+                const long long off = r * C + cv * 8;
+                vy[u] = ld8(y + off);
+                if (res) vr[u] = ld8(res + off);
+            }
         }
-        if (relu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r >= M) break;
+            float f[8];
+            unpack8(vy[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sh[i];
+            if (res) {
+                float rr[8];
+                unpack8(vr[u], rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += rr[i];
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            st8(z + r * C + cv * 8, pack8(f));
         }
-        st8(z + off, pack8(f));
     }
 }
 
@@ -162,25 +196,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
             dgamma[cv * 8 + i] = sums[C + cv * 8 + i];
         }
     }
-    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < M; r += (long long)gridDim.x * rows_per_iter) {
-        const long long off = r * C + cv * 8;
-        float d[8], yy[8];
-        unpack8(ld8(dz + off), d);
-        unpack8(ld8(y + off), yy);
-        if (relu) {
-            float zz[8];
-            unpack8(ld8(z + off), zz);
+    const long long rstride = (long long)gridDim.x * rows_per_iter;
+    for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
+        bf16x8 vd[BN_UNROLL], vy[BN_UNROLL], vz[BN_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) d[i] = 0.f;
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r < M) {
+                const long long off = r * C + cv * 8;
+                vd[u] = ld8(dz + off);
+                vy[u] = ld8(y + off);
+                if (relu) vz[u] = ld8(z + off);
+            }
         }
-        if (dres) st8(dres + off, pack8(d));
-        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xh = (yy[i] - mean[i]) * invstd[i];
-            o[i] = g[i] * (d[i] - k1[i] - xh * k2[i]);
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * rstride;
+            if (r >= M) break;
+            const long long off = r * C + cv * 8;
+            float d[8], yy[8];
+            unpack8(vd[u], d);
+            unpack8(vy[u], yy);
+            if (relu) {
+                float zz[8];
+                unpack8(vz[u], zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) d[i] = 0.f;
+            }
+            if (dres) st8(dres + off, pack8(d));
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xh = (yy[i] - mean[i]) * invstd[i];
+                o[i] = g[i] * (d[i] - k1[i] - xh * k2[i]);
+            }
+            st8(dy + off, pack8(o));
         }
-        st8(dy + off, pack8(o));
     }
 }
 
@@ -238,44 +289,57 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
-                                                            bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, long long rows, int D) {
-    extern __shared__ float sh[];   // [2][D] block partials of dgamma / dbeta
+// Backward: one warp per row, NV vectors of 8 per lane (D = 256*NV max).  dx = rstd*(dy*g - c1 - xhat*c2) (+ dres: the
+// skip-connection gradient of the pre-norm residual block, fused here instead of a separate add pass).
+// dgamma/dbeta partials stay in registers across the warp's rows, are combined across the block's warps through a
+// conflict-free shared layout (no shared atomics) and leave the block as one global atomic per column.
+template <int NV>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                               const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                               const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               long long rows, int D) {
+    extern __shared__ float sh[];   // [2][8][D/8]: element (col = vi*8+i) of plane p lives at p*D + i*(D/8) + vi
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const int nvec = D >> 3;
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
-    float ag[LN_MAXV][8], ab[LN_MAXV][8];
+    float ag[NV][8], ab[NV][8];
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k)
+    for (int k = 0; k < NV; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) ag[k][i] = ab[k][i] = 0.f;
-
-    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+    for (long long row = (long long)blockIdx.x * warps_per_block + warp; row < rows;
          row += (long long)gridDim.x * warps_per_block) {
+        bf16x8 xr[NV], dr[NV], rr[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) {
+                xr[k] = ld8(x + row * D + vi * 8);
+                dr[k] = ld8(dy + row * D + vi * 8);
+                if (dres) rr[k] = ld8(dres + row * D + vi * 8);
+            }
+        }
         const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
-        float xh[LN_MAXV][8], dxh[LN_MAXV][8];
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < NV; ++k) {
             const int vi = lane + k * 32;
             if (vi < nvec) {
                 float xv[8], dv[8];
-                unpack8(ld8(x + row * D + vi * 8), xv);
-                unpack8(ld8(dy + row * D + vi * 8), dv);
+                unpack8(xr[k], xv);
+                unpack8(dr[k], dv);
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[k][i] = (xv[i] - mean) * rstd;
-                    dxh[k][i] = dv[i] * gg[i];
-                    c1 += dxh[k][i];
-                    c2 += dxh[k][i] * xh[k][i];
-                    ag[k][i] += dv[i] * xh[k][i];
+                    const float xh = (xv[i] - mean) * rstd;
+                    const float dg = dv[i] * gg[i];
+                    c1 += dg;
+                    c2 += dg * xh;
+                    ag[k][i] += dv[i] * xh;
                     ab[k][i] += dv[i];
                 }
             }
@@ -283,31 +347,49 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         c1 = warp_sum(c1) / (float)D;
         c2 = warp_sum(c2) / (float)D;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < NV; ++k) {
             const int vi = lane + k * 32;
             if (vi < nvec) {
-                float o[8];
+                float xv[8], dv[8], o[8];
+                unpack8(xr[k], xv);
+                unpack8(dr[k], dv);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = rstd * (dxh[k][i] - c1 - xh[k][i] * c2);
+                for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[i] * gg[i] - c1 - (xv[i] - mean) * rstd * c2);
+                if (dres) {
+                    float rv[8];
+                    unpack8(rr[k], rv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] += rv[i];
+                }
                 st8(dx + row * D + vi * 8, pack8(o));
             }
         }
     }
+    for (int w = 0; w < warps_per_block; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
-        const int vi = lane + k * 32;
-        if (vi < nvec) {
+            for (int k = 0; k < NV; ++k) {
+                const int vi = lane + k * 32;
+                if (vi < nvec) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                atomicAdd(&sh[vi * 8 + i], ag[k][i]);
-                atomicAdd(&sh[D + vi * 8 + i], ab[k][i]);
+                    for (int i = 0; i < 8; ++i) {
+                        float* pg = sh + i * nvec + vi;
+                        float* pb = sh + D + i * nvec + vi;
+                        if (w == 0) { *pg = ag[k][i]; *pb = ab[k][i]; }
+                        else { *pg += ag[k][i]; *pb += ab[k][i]; }
+                    }
+                }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        atomicAdd(dgamma + i, sh[i]);
-        atomicAdd(dbeta + i, sh[D + i]);
+    for (int t = threadIdx.x; t < D; t += blockDim.x) {
+        const int i = t / nvec, vi = t - i * nvec;
+        atomicAdd(dgamma + vi * 8 + i, sh[t]);
+        atomicAdd(dbeta + vi * 8 + i, sh[D + t]);
     }
 }
 
@@ -433,12 +515,22 @@ extern "C" int dfu_layernorm(const void* x, const float* gamma, const float* bet
     DFU_CHECK_LAUNCH("layernorm");
     return DFU_OK;
 }
-extern "C" int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, void* dx,
-                                 float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream) {
+extern "C" int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, const void* dres,
+                                 void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream) {
     DFU_CHECK_ARG(dy && x && gamma && stats && dx && dgamma && dbeta && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256,
                   "dfu_layernorm_bwd: unsupported D=%d", D);
-    layernorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 4), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
-        (const bf16*)dy, (const bf16*)x, gamma, stats, (bf16*)dx, dgamma, dbeta, rows, D);
+    const int grid = grid_cap((rows + 7) / 8, 2);
+    const size_t smem = 2 * (size_t)D * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nv = (D / 8 + 31) / 32;
+#define DFU_LN_BWD(NV)                                                                                              \
+    layernorm_bwd_kernel<NV><<<grid, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, stats, (const bf16*)dres, \
+                                                      (bf16*)dx, dgamma, dbeta, rows, D)
+    if (nv == 1) DFU_LN_BWD(1);
+    else if (nv == 2) DFU_LN_BWD(2);
+    else if (nv == 3) DFU_LN_BWD(3);
+    else DFU_LN_BWD(4);
+#undef DFU_LN_BWD
     DFU_CHECK_LAUNCH("layernorm_bwd");
     return DFU_OK;
 }

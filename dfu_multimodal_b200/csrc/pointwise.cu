@@ -51,6 +51,18 @@ __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a,
     }
 }
 
+// Zero fill: 16-byte stores over the aligned body, byte stores for the (at most 15-byte) head and tail.
+__global__ void __launch_bounds__(256) zero_kernel(unsigned char* __restrict__ p, long long bytes) {
+    const long long head = ((16 - ((uintptr_t)p & 15)) & 15) < (unsigned long long)bytes ? ((16 - ((uintptr_t)p & 15)) & 15) : bytes;
+    const long long nv = (bytes - head) >> 4;
+    uint4* body = reinterpret_cast<uint4*>(p + head);
+    GRID_STRIDE(i, nv) body[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0) {
+        for (long long i = threadIdx.x; i < head; i += blockDim.x) p[i] = 0;
+        for (long long i = head + (nv << 4) + threadIdx.x; i < bytes; i += blockDim.x) p[i] = 0;
+    }
+}
+
 // Column sums of x[M, N] (row stride ld) added into out[N].  Block = 32 column-vectors x 8 row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M, int N,
                                                      long long ld, int rows_per_block) {
@@ -336,6 +348,13 @@ int launch_binary(const void* a, const void* b, void* out, long long n, void* st
 
 }  // namespace
 
+extern "C" int dfu_zero(void* p, int64_t bytes, void* stream) {
+    DFU_CHECK_ARG(p && bytes >= 0, "dfu_zero: bad args");
+    if (bytes == 0) return DFU_OK;
+    zero_kernel<<<grid_for((bytes + 15) / 16, 256), 256, 0, (cudaStream_t)stream>>>((unsigned char*)p, bytes);
+    DFU_CHECK_LAUNCH("dfu_zero");
+    return DFU_OK;
+}
 extern "C" int dfu_relu(const void* x, void* y, int64_t n, void* stream) { return launch_binary<0>(x, nullptr, y, n, stream, "dfu_relu"); }
 extern "C" int dfu_gelu(const void* x, void* y, int64_t n, void* stream) { return launch_binary<4>(x, nullptr, y, n, stream, "dfu_gelu"); }
 extern "C" int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {

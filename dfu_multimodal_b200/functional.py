@@ -109,7 +109,9 @@ class Conv2dFn(Function):
     shapes go through im2col.  Replaces torchvision ResNet's nn.Conv2d (cudnn fwd/dgrad/wgrad)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, pad):
+    def forward(ctx, x, weight, stride, pad, fork=False):
+        """fork=True additionally returns x itself (the Bottleneck's skip connection); its gradient is then added
+        in the dgrad GEMM epilogue instead of by a separate pass."""
         xn = ops.as_nhwc(x)
         B, H, W, C = xn.shape
         Cout, Cin, R, S = weight.shape
@@ -124,10 +126,12 @@ class Conv2dFn(Function):
         y, _ = ops.linear_forward(A, wm)
         ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct)
         ctx.save_for_backward(A, weight)
-        return y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+        ctx.fork = fork
+        out = y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+        return (out, x.view_as(x)) if fork else out
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gskip=None):
         A, weight = ctx.saved_tensors
         B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct = ctx.geom
         g = ops.as_nhwc(gy).reshape(B * Ho * Wo, Cout)
@@ -140,13 +144,17 @@ class Conv2dFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wm = conv_weight_matrix(weight)
-            dcol = ops.linear_dgrad(g, wm, ldc)
+            skip = ops.as_nhwc(gskip).reshape(B * H * W, C) if gskip is not None else None
             if direct:
-                dx = dcol.view(B, H, W, C)
+                dx = ops.linear_dgrad(g, wm, ldc, res=skip).view(B, H, W, C)
             else:
-                dx = ops.col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
+                dx = ops.col2im(ops.linear_dgrad(g, wm, ldc), B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
+                if skip is not None:
+                    dx = ops.add(dx, skip.view(B, H, W, C))
             dx = dx.permute(0, 3, 1, 2)
-        return dx, dw, None, None
+        elif gskip is not None:
+            dx = gskip
+        return dx, dw, None, None, None
 
 
 class BatchNormActFn(Function):
@@ -333,6 +341,29 @@ class LayerNormFn(Function):
         return dx.view(gy.shape), dg, db, None
 
 
+class LayerNormForkFn(Function):
+    """(LayerNorm(x), x): the pre-norm residual block's fork.  Backward folds the skip-connection gradient into the
+    LayerNorm backward kernel (dx = LN'(g_norm) + g_skip), so no separate add pass runs."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        y, stats = ops.layernorm(x2, gamma, beta, eps)
+        ctx.save_for_backward(x2, gamma, stats)
+        return y.view(x.shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gy, gskip):
+        x2, gamma, stats = ctx.saved_tensors
+        D = x2.shape[1]
+        if gy is None:
+            return gskip, None, None, None
+        dres = _as_bf16_2d(gskip, D) if gskip is not None else None
+        dx, dg, db = ops.layernorm_bwd(_as_bf16_2d(gy, D), x2, gamma, stats, dres)
+        return dx.view(gy.shape), dg, db, None
+
+
 class AttentionFn(Function):
     """softmax(q k^T / 8) v over 197 tokens per (batch, head) on the packed qkv projection (timm Attention)."""
 
@@ -383,7 +414,7 @@ class ClsTokenFn(Function):
     @staticmethod
     def backward(ctx, g):
         B, T, D = ctx.cfg
-        dx = torch.zeros((B, T, D), dtype=BF16, device=g.device)
+        dx = ops.zeros((B, T, D), BF16, g.device)
         ops.copy2d(_as_bf16_2d(g, D), D, dx, T * D, B, D)
         return dx
 

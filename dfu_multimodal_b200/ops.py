@@ -54,6 +54,68 @@ def _p(t, elem_offset=0):
     return t.data_ptr() + elem_offset * t.element_size()
 
 
+# ------------------------------------------------------------------------------------------ zeroed accumulators
+class _ZeroArena:
+    """Accumulators that must start at zero (BN/LN partial sums, bias gradients, split-K wgrad targets) are carved
+    out of one arena that a single dfu_zero launch clears at the start of a train step, instead of one fill kernel
+    per buffer (~300 per step).  Only active between begin_step() calls made by train.TrainStep, whose step frees
+    every gradient (zero_grad(set_to_none=True)) before the arena is cleared again; outside of it zeros() clears
+    each buffer with its own dfu_zero launch."""
+
+    ALIGN = 256
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.need = 0
+        self.active = False
+
+    def begin_step(self, device):
+        want = max(self.need, self.off)
+        if self.buf is None or self.buf.numel() < want or self.buf.device != device:
+            self.buf = torch.empty(int(want * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
+        self.need = want
+        used = min(self.buf.numel(), max(want, 1))
+        check(_L().dfu_zero(_p(self.buf), used, _st()), "dfu_zero")
+        _count()
+        self.cleared = used
+        self.off = 0
+        self.active = True
+
+    def end_step(self):
+        self.active = False
+
+    def take(self, nbytes):
+        start = (self.off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        end = start + nbytes
+        self.off = end
+        if self.buf is None or end > self.cleared:
+            return None                      # arena too small this step: grows at the next begin_step
+        return self.buf[start:end]
+
+
+ZERO_ARENA = _ZeroArena()
+
+
+def zeros(shape, dtype, device):
+    """Zero-initialised accumulator (see _ZeroArena)."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= d
+    esz = torch.empty((), dtype=dtype).element_size()
+    if ZERO_ARENA.active and ZERO_ARENA.buf is not None and ZERO_ARENA.buf.device == device:
+        raw = ZERO_ARENA.take(n * esz)
+        if raw is not None:
+            return raw.view(dtype).view(shape)
+    out = torch.empty(shape, dtype=dtype, device=device)
+    if n:
+        check(_L().dfu_zero(_p(out), n * esz, _st()), "dfu_zero")
+        _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_off=0, d_off=0, nb0=1, nb1=1,
          sa=(0, 0), sb=(0, 0), sd=(0, 0), accumulate=False, aux=None, bias=None, res=None, ldr=0, sr=(0, 0),
@@ -105,11 +167,12 @@ def linear_forward(x2d, w, bias=None, act=0, res=None, want_aux=False, out_dtype
     return y, aux
 
 
-def linear_dgrad(dy2d, w, K):
-    """dx[M,K] = dy2d[M,N] @ w[N,:K]  (w row-major [N, ldw]: MN-major B operand)."""
+def linear_dgrad(dy2d, w, K, res=None):
+    """dx[M,K] = dy2d[M,N] @ w[N,:K] (+ res)  (w row-major [N, ldw]: MN-major B operand)."""
     M, N = dy2d.shape
     dx = torch.empty((M, K), dtype=BF16, device=dy2d.device)
-    gemm(dy2d, w, dx, M=M, N=K, K=N, lda=dy2d.stride(0), ldb=w.stride(0), b_major=1, ldd=K)
+    gemm(dy2d, w, dx, M=M, N=K, K=N, lda=dy2d.stride(0), ldb=w.stride(0), b_major=1, ldd=K, res=res,
+         ldr=(res.stride(0) if res is not None else 0))
     return dx
 
 
@@ -118,7 +181,7 @@ def linear_wgrad(dy2d, x2d, Kp=None):
     M, N = dy2d.shape
     Kx = x2d.shape[1] if Kp is None else Kp
     if _wgrad_needs_splitk(N, Kx):
-        dw = torch.zeros((N, Kx), dtype=F32, device=dy2d.device)
+        dw = zeros((N, Kx), F32, dy2d.device)
         acc = True
     else:
         dw = torch.empty((N, Kx), dtype=F32, device=dy2d.device)
@@ -243,7 +306,7 @@ def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, tr
     mean_invstd = torch.empty(2 * C, dtype=F32, device=dev)
     L = _L()
     if training:
-        sums = torch.zeros(2 * C, dtype=F32, device=dev)
+        sums = zeros(2 * C, F32, dev)
         check(L.dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
         check(L.dfu_bn_finalize(_p(sums), _p(mean_invstd), _p(running_mean), _p(running_var), _p(nbt), M, C, eps,
                                 momentum, _st()), "bn_finalize")
@@ -262,7 +325,7 @@ def bn_backward(dz2d, z2d, y2d, mean_invstd, gamma, relu, training, want_dres):
     M, C = y2d.shape
     dev = y2d.device
     L = _L()
-    sums = torch.zeros(2 * C, dtype=F32, device=dev)
+    sums = zeros(2 * C, F32, dev)
     check(L.dfu_bn_bwd_reduce(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(sums), M, C, 1 if relu else 0, _st()),
           "bn_bwd_reduce")
     dy = torch.empty_like(y2d)
@@ -358,7 +421,7 @@ def gelu_bwd(dy, h):
 
 def colsum(x2d):
     M, N = x2d.shape
-    out = torch.zeros(N, dtype=F32, device=x2d.device)
+    out = zeros(N, F32, x2d.device)
     check(_L().dfu_colsum(_p(x2d), _p(out), M, N, x2d.stride(0), _st()), "colsum")
     _count()
     return out
@@ -437,8 +500,8 @@ def vit_assemble(patch_out, cls, pos, B, T, D):
 def vit_assemble_bwd(dtokens, B, T, D):
     dev = dtokens.device
     dpatch = torch.empty((B * (T - 1), D), dtype=BF16, device=dev)
-    dcls = torch.zeros(D, dtype=F32, device=dev)
-    dpos = torch.zeros(T * D, dtype=F32, device=dev)
+    dcls = zeros(D, F32, dev)
+    dpos = zeros(T * D, F32, dev)
     check(_L().dfu_vit_assemble_bwd(_p(dtokens), _p(dpatch), _p(dcls), _p(dpos), B, T, D, _st()), "vit_assemble_bwd")
     _count()
     return dpatch, dcls, dpos
@@ -453,13 +516,14 @@ def layernorm(x2d, gamma, beta, eps, want_stats=True):
     return y, stats
 
 
-def layernorm_bwd(dy2d, x2d, gamma, stats):
+def layernorm_bwd(dy2d, x2d, gamma, stats, dres=None):
+    """dx = LN'(dy) (+ dres, the skip-connection gradient), dgamma, dbeta."""
     rows, D = x2d.shape
     dx = torch.empty_like(x2d)
-    dgamma = torch.zeros(D, dtype=F32, device=x2d.device)
-    dbeta = torch.zeros(D, dtype=F32, device=x2d.device)
-    check(_L().dfu_layernorm_bwd(_p(dy2d), _p(x2d), _p(gamma), _p(stats), _p(dx), _p(dgamma), _p(dbeta), rows, D,
-                                 _st()), "layernorm_bwd")
+    dgb = zeros((2, D), F32, x2d.device)
+    dgamma, dbeta = dgb[0], dgb[1]
+    check(_L().dfu_layernorm_bwd(_p(dy2d), _p(x2d), _p(gamma), _p(stats), _p(dres), _p(dx), _p(dgamma), _p(dbeta),
+                                 rows, D, _st()), "layernorm_bwd")
     _count()
     return dx, dgamma, dbeta
 

@@ -10,10 +10,13 @@ from .nn import (DfuAvgPoolFlatten, DfuBatchNorm2d, DfuConv2d, DfuLinear, DfuMax
                  has_hooks, to_act)
 
 
-def _conv_bn(x, conv, bn, relu, res=None):
-    y = Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0])
+def _bn(y, bn, relu, res=None):
     return Fn.BatchNormActFn.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var,
                                    bn.num_batches_tracked, relu, bn.training, bn.eps, bn.momentum)
+
+
+def _conv_bn(x, conv, bn, relu, res=None):
+    return _bn(Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0]), bn, relu, res)
 
 
 class DfuBottleneck(nn.Module):
@@ -35,9 +38,13 @@ class DfuBottleneck(nn.Module):
         x = to_act(x)
         if has_hooks(self):
             return self._forward_modules(x)
-        needs_fork = torch.is_grad_enabled() and x.requires_grad
-        xm, xs = Fn.Fork.apply(x) if needs_fork else (x, x)
-        out = _conv_bn(xm, self.conv1, self.bn1, True)
+        if torch.is_grad_enabled() and x.requires_grad:
+            # conv1 and the skip connection fork here; the skip gradient is added in conv1's dgrad GEMM epilogue
+            y1, xs = Fn.Conv2dFn.apply(x, self.conv1.weight, 1, 0, True)
+            out = _bn(y1, self.bn1, True)
+        else:
+            xs = x
+            out = _conv_bn(x, self.conv1, self.bn1, True)
         out = _conv_bn(out, self.conv2, self.bn2, True)
         identity = xs if self.downsample is None else _conv_bn(xs, self.downsample[0], self.downsample[1], False)
         return _conv_bn(out, self.conv3, self.bn3, True, res=identity)

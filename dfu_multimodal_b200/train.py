@@ -23,6 +23,7 @@ class TrainStep:
     # -- the step itself (eager) -------------------------------------------------------------------------
     def _step(self, rgb, thermal, labels):
         self.optimizer.zero_grad(set_to_none=True)
+        ops.ZERO_ARENA.begin_step(rgb.device)      # one dfu_zero launch clears every accumulator of the step
         if self.bucketer is not None:
             self.bucketer.begin_step()
         ops.DROPOUT.tick(rgb.device)
@@ -32,6 +33,7 @@ class TrainStep:
         if self.bucketer is not None:
             self.bucketer.finish_step()
         self.optimizer.step()
+        ops.ZERO_ARENA.end_step()
         return loss.detach(), logits.detach()
 
     def _capture(self, rgb, thermal, labels):

@@ -78,16 +78,25 @@ class DfuBlock(nn.Module):
     def forward(self, x):
         x = to_act(x)
         fork = torch.is_grad_enabled() and x.requires_grad
-        if has_hooks(self.attn, self.mlp):
+        if has_hooks(self.attn, self.mlp, self.norm1, self.norm2):
             # unfused residual adds so hooks on attn / mlp observe the branch output alone (timm Block.forward)
             xa, xs = Fn.Fork.apply(x) if fork else (x, x)
             x = Fn.AddFn.apply(xs, self.attn(self.norm1(xa)))
             xa, xs = Fn.Fork.apply(x) if fork else (x, x)
             return Fn.AddFn.apply(xs, self.mlp(self.norm2(xa)))
-        xa, xs = Fn.Fork.apply(x) if fork else (x, x)
-        x = self.attn(self.norm1(xa), res=xs)             # residual fused into the proj GEMM epilogue
-        xa, xs = Fn.Fork.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else (x, x)
-        return self.mlp(self.norm2(xa), res=xs)           # residual fused into the fc2 GEMM epilogue
+        # the skip connection forks inside LayerNormForkFn (its gradient is added by the LayerNorm backward kernel)
+        # and rejoins in the proj / fc2 GEMM epilogue
+        n1, n2 = self.norm1, self.norm2
+        if fork:
+            xa, xs = Fn.LayerNormForkFn.apply(x, n1.weight, n1.bias, n1.eps)
+        else:
+            xa, xs = n1(x), x
+        x = self.attn(xa, res=xs)
+        if torch.is_grad_enabled() and x.requires_grad:
+            xa, xs = Fn.LayerNormForkFn.apply(x, n2.weight, n2.bias, n2.eps)
+        else:
+            xa, xs = n2(x), x
+        return self.mlp(xa, res=xs)
 
 
 class DfuVisionTransformer(nn.Module):

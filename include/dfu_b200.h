@@ -107,6 +107,8 @@ int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t B
 /* global average pool [B,HW,C] -> [B, C] written with row stride ldo (lets it land inside the concat buffer) */
 int dfu_avgpool(const void* x, void* out, int32_t B, int32_t HW, int32_t C, int64_t ldo, void* stream);
 int dfu_avgpool_bwd(const void* dout, int64_t ldo, void* dx, int32_t B, int32_t HW, int32_t C, void* stream);
+/* zero `bytes` bytes at p (aten::zeros / zero_ for accumulators: BN/LN sums, split-K wgrad targets, bias grads). */
+int dfu_zero(void* p, int64_t bytes, void* stream);
 int dfu_relu(const void* x, void* y, int64_t n, void* stream);
 int dfu_gelu(const void* x, void* y, int64_t n, void* stream);
 int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
@@ -137,9 +139,10 @@ int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dcls, float* 
 /* LayerNorm over the last dim (eps 1e-6 in timm): y bf16, stats[2*rows] = (mean, rstd) fp32. */
 int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
                   int32_t D, float eps, void* stream);
-/* dx (bf16), dgamma/dbeta += (fp32, caller zeroes). */
-int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, void* dx,
-                      float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream);
+/* dx (bf16) = LN'(dy) [+ dres: the skip-connection gradient of the pre-norm residual block, may be null];
+ * dgamma/dbeta += (fp32, caller zeroes). */
+int dfu_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats, const void* dres,
+                      void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream);
 /* Row softmax of S[rows, ld] over the first n columns (fp32 math), pad columns written as 0. In place allowed. */
 int dfu_softmax_rows(const void* s, void* p, int64_t rows, int32_t n, int64_t ld, void* stream);
 /* dS = P * (dP - rowsum(dP*P)) * scale */

@@ -148,7 +148,7 @@ def test_layout_conversions(ops, dev):
     assert torch.equal(ops.unpatchify_f32(dp, 2), back)
 
 
-@pytest.mark.parametrize("C,R,stride,pad,H", [(64, 3, 1, 1, 14), (64, 3, 2, 1, 14), (3, 7, 2, 3, 32), (128, 1, 2, 0, 8),
+@pytest.mark.parametrize("C,R,stride,pad,H", [(64, 3, 1, 1, 14), (64, 3, 2, 1, 14), (3, 7, 2, 3, 32), (3, 7, 2, 3, 224), (128, 1, 2, 0, 8),
                                               (256, 3, 1, 1, 7)])
 def test_im2col_col2im(ops, dev, C, R, stride, pad, H):
     x = rnd(dev, 2, C, H, H)
@@ -213,6 +213,33 @@ def test_layernorm(ops, dev, rows, D):
     close(dx, xf.grad, 3 * BF16_EPS, 2e-3)
     close(dg, gf.grad, 1e-3, 1e-3)
     close(db, bf.grad, 1e-3, 1e-3)
+    # fused skip-connection gradient: dx = LN'(dy) + dres
+    dres = rnd(dev, rows, D)
+    dx2, dg2, db2 = ops.layernorm_bwd(dy, x, g, stats, dres)
+    close(dx2, xf.grad + dres.float(), 3 * BF16_EPS, 2e-3)
+    close(dg2, gf.grad, 1e-3, 1e-3)
+    close(db2, bf.grad, 1e-3, 1e-3)
+
+
+def test_zero_fill_and_arena(ops, dev):
+    for n in (1, 15, 16, 17, 4099):
+        raw = torch.full((n + 32,), 7, dtype=torch.uint8, device=dev)
+        from dfu_multimodal_b200._lib import check
+        check(ops._L().dfu_zero(raw.data_ptr() + 3, n, torch.cuda.current_stream().cuda_stream), "dfu_zero")
+        assert int(raw[:3].sum()) == 21 and int(raw[3:3 + n].sum()) == 0 and int(raw[3 + n:].min()) == 7
+    z = ops.zeros((5, 7), torch.float32, dev)
+    assert z.shape == (5, 7) and float(z.abs().sum()) == 0.0
+    arena = ops.ZERO_ARENA
+    for _ in range(3):                       # the arena sizes itself from the previous step's demand
+        arena.begin_step(dev)
+        a = ops.zeros((1000,), torch.float32, dev)
+        b = ops.zeros((3, 333), torch.bfloat16, dev)
+        assert float(a.abs().sum()) == 0.0 and float(b.float().abs().sum()) == 0.0
+        a.fill_(1.0)
+        b.fill_(1.0)
+        arena.end_step()
+    assert a.data_ptr() % 256 == 0 and b.data_ptr() % 256 == 0
+    assert a.untyped_storage().data_ptr() == arena.buf.untyped_storage().data_ptr()
 
 
 # ----------------------------------------------------------------------------------------------- pooling / pointwise
