@@ -370,16 +370,16 @@ class AttentionFn(Function):
     @staticmethod
     def forward(ctx, qkv, B, T, H, scale):
         q2 = qkv.reshape(B * T, -1)
-        out, P = ops.attention_forward(q2, B, T, H, scale)
+        out, saved = ops.attention_forward(q2, B, T, H, scale)
         ctx.cfg = (B, T, H, scale)
-        ctx.save_for_backward(q2, P)
+        ctx.save_for_backward(q2, saved, out)
         return out.view(B, T, H * 64)
 
     @staticmethod
     def backward(ctx, g):
-        q2, P = ctx.saved_tensors
+        q2, saved, out = ctx.saved_tensors
         B, T, H, scale = ctx.cfg
-        dqkv = ops.attention_backward(q2, P, _as_bf16_2d(g, H * 64), B, T, H, scale)
+        dqkv = ops.attention_backward(q2, saved, _as_bf16_2d(g, H * 64), B, T, H, scale, out=out)
         return dqkv.view(B, T, -1), None, None, None, None
 
 

@@ -528,9 +528,28 @@ def layernorm_bwd(dy2d, x2d, gamma, stats, dres=None):
     return dx, dgamma, dbeta
 
 
+# "fused": one tcgen05 kernel per direction (attention.cu); "unfused": batched GEMM + row-softmax kernels.
+_ATTN_IMPL = os.environ.get("DFU_ATTN_IMPL", "fused")
+
+
+def set_attention_impl(impl):
+    global _ATTN_IMPL
+    assert impl in ("fused", "unfused")
+    _ATTN_IMPL = impl
+
+
 def attention_forward(qkv, B, T, H, scale):
     """softmax(q k^T * scale) v per (batch, head); qkv [B*T, 3*H*64] bf16 in timm order [3][H][64].
-    Returns (out [B*T, H*64], P [B,H,T,ldp]) -- P is kept for the backward pass."""
+    Returns (out [B*T, H*64], saved) where `saved` is what the backward pass needs: the fp32 row log-sum-exp
+    [B,H,T] of the fused kernel, or the bf16 probabilities [B,H,T,ldp] of the unfused path."""
+    if _ATTN_IMPL == "fused" and 128 < T <= 208:
+        _need_cuda(qkv)
+        assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.shape == (B * T, 3 * H * 64)
+        out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+        check(_L().dfu_attention_fwd(_p(qkv), _p(out), _p(lse), B, T, H, scale, _st()), "attention_fwd")
+        _count()
+        return out, lse
     hd = 64
     D3 = 3 * H * hd
     ldp = (T + 7) // 8 * 8
@@ -546,7 +565,17 @@ def attention_forward(qkv, B, T, H, scale):
     return out, P
 
 
-def attention_backward(qkv, P, dout, B, T, H, scale):
+def attention_backward(qkv, saved, dout, B, T, H, scale, out=None):
+    """dqkv from the upstream gradient of the attention output; `saved` as returned by attention_forward."""
+    if saved.dtype == F32:
+        assert out is not None, "the fused backward needs the forward output"
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        check(_L().dfu_attention_bwd(_p(qkv), _p(out), _p(dout), _p(saved), _p(dqkv), B, T, H, scale, _st()),
+              "attention_bwd")
+        _count()
+        return dqkv
+    P = saved
     hd = 64
     D3 = 3 * H * hd
     ldp = P.shape[-1]

@@ -103,9 +103,17 @@ def test_gemm_rejects_bad_arguments(ops, dev):
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("B", [1, 3])
-def test_attention_forward_backward(ops, dev, B):
-    T, H = 197, 12
+@pytest.mark.parametrize("impl", ["fused", "unfused"])
+@pytest.mark.parametrize("B,T,H", [(1, 197, 12), (3, 197, 12), (26, 197, 12), (2, 208, 3), (2, 129, 2), (5, 150, 1)])
+def test_attention_forward_backward(ops, dev, B, T, H, impl):
+    ops.set_attention_impl(impl)
+    try:
+        _attention_case(ops, dev, B, T, H)
+    finally:
+        ops.set_attention_impl("fused")
+
+
+def _attention_case(ops, dev, B, T, H):
     qkv = rnd(dev, B * T, 3 * H * 64, scale=0.5)
     out, P = ops.attention_forward(qkv, B, T, H, 0.125)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
@@ -114,7 +122,10 @@ def test_attention_forward_backward(ops, dev, B):
     close(out, o, 1e-2, 1e-3)
     do = rnd(dev, B * T, H * 64)
     o.backward(do.float())
-    dqkv = ops.attention_backward(qkv, P, do, B, T, H, 0.125)
+    if P.dtype == torch.float32:      # fused path saves the row log-sum-exp
+        s_ref = (q @ k.transpose(-1, -2) * 0.125).detach()
+        close(P, torch.logsumexp(s_ref, -1), 1e-3, 2e-2)
+    dqkv = ops.attention_backward(qkv, P, do, B, T, H, 0.125, out=out)
     dref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * T, 3 * H * 64)
     close(dqkv, dref, 2e-2, 1e-3)
 
