@@ -87,6 +87,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 mbar_wait(&v_empty, ph ^ 1);
                 mbar_expect_tx(&v_full, KV_BYTES);
                 tma_load_2d(&map_kv, &v_full, smem + F_V, (2 * H + h) * HD, row0);
+                if (w + (int)gridDim.x < items) {        // next head's operands -> L2 while this one is computed
+                    const int wn = w + gridDim.x, bn = wn / H, hn = wn - bn * H;
+                    tma_prefetch_2d(&map_q, hn * HD, bn * T);
+                    tma_prefetch_2d(&map_q, hn * HD, bn * T + 128);
+                    tma_prefetch_2d(&map_kv, (H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&map_kv, (2 * H + hn) * HD, bn * T);
+                }
             }
         }
     } else if (warp_idx == 1) {
@@ -282,6 +289,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
                 tma_load_2d(&map_qkv, &ops_full, smem + B_K, (H + h) * HD, row0);
                 tma_load_2d(&map_qkv, &ops_full, smem + B_V, (2 * H + h) * HD, row0);
                 tma_load_2d(&map_do, &ops_full, smem + B_DO, h * HD, row0);
+                if (w + (int)gridDim.x < items) {        // next head's operands -> L2 while this one is computed
+                    const int wn = w + gridDim.x, bn = wn / H, hn = wn - bn * H;
+                    tma_prefetch_2d(&map_qkv, hn * HD, bn * T);
+                    tma_prefetch_2d(&map_qkv, (H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&map_qkv, (2 * H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&map_do, hn * HD, bn * T);
+                }
             }
         }
     } else if (warp_idx == 1) {
