@@ -23,7 +23,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int MAX_BLOCK_N = 256;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;            // ring depth (3 when a second staging slab per epilogue warp is needed for aux)
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_TILE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KB
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;   // 48 KB
@@ -54,6 +54,7 @@ struct GemmParams {
     int act;
     int vec_ok;
     int tma_store;     // epilogue goes through swizzled smem + TMA store / reduce-add
+    int stages;        // smem ring depth actually used (<= STAGES)
     int res_vec;
 };
 
@@ -158,6 +159,33 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// exact-erf GELU through Abramowitz-Stegun 7.1.28 (|erf error| <= 3e-7): one MUFU.RCP and ~14 FP32 ops per element
+// instead of erff(); gelu(x) = relu(x) - 0.5 |x| / (1 + a1 z + ... + a6 z^6)^16 with z = |x| / sqrt(2).
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
+    float q = 0.0000430638f;
+    q = fmaf(q, z, 0.0002765672f);
+    q = fmaf(q, z, 0.0001520143f);
+    q = fmaf(q, z, 0.0092705272f);
+    q = fmaf(q, z, 0.0422820123f);
+    q = fmaf(q, z, 0.0705230784f);
+    q = fmaf(q, z, 1.0f);
+    q = q * q; q = q * q; q = q * q; q = q * q;
+    float r;                               // q = inf for large |x| -> r = 0
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+    return fmaf(-0.5f * ax, r, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ bf16x8 ld_nc16(const bf16* p) {
+    uint4 u;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+    return *reinterpret_cast<bf16x8*>(&u);
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(v);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
 // ----------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -236,7 +264,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         for (int j = 0; j < p.block_n / 64; ++j)
                             tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, n0 + j * 64, k0, z0, z1);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -273,7 +301,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
             }
@@ -285,7 +313,6 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
         const int n_chunks = p.block_n / 32;
         int it = 0;
-        int buf = 0;             // staging double buffer (TMA store of slab i overlaps the fill of slab i+1)
         for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
             long long t = w;
             const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
@@ -302,124 +329,152 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const long long d_off = (long long)z1 * p.sd1 + (long long)z0 * p.sd0 + (long long)m * p.ldd;
             const long long r_off = (long long)z1 * p.sr1 + (long long)z0 * p.sr0 + (long long)m * p.ldr;
             if (p.tma_store) {
-                // TMEM -> registers -> bias/act/residual -> swizzled smem slab (32 rows x 128 B) -> TMA store.
-                // The two warps of a lane quarter alternate slabs; TMA clips rows >= M and columns >= N.
-                uint8_t* const stg0 = smem + STAGES * STAGE_BYTES + ew * EPI_BUFS * STG_BYTES;
-                uint8_t* stg = stg0 + buf * STG_BYTES;
+                // TMEM -> registers -> bias / act / residual -> swizzled smem slab (32 rows x 128 B) -> TMA store.
+                // The two warps of a lane quarter alternate slabs; TMA clips rows >= M and columns >= N.  Everything
+                // with latency is issued ahead of its use: the next 32-column TMEM load while the current chunk is in
+                // the FP32 pipes, and the next slab's residual row (8 x 16 B per thread) one slab early.
+                uint8_t* const stg_out = smem + p.stages * STAGE_BYTES + ew * (p.aux ? 2 : 1) * STG_BYTES;
+                uint8_t* const stg_aux = stg_out + STG_BYTES;
+                const uint32_t sa_out = smem_u32(stg_out) + lane * 128, sa_aux = sa_out + STG_BYTES;
                 const int slab_cols = p.d_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
-                const int chunks = p.d_fp32 ? 1 : 2;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
-                for (int sl = group; sl < n_slabs; sl += 2) {
-                    const int ncol0 = n_tile * p.block_n + sl * slab_cols;
-                    if (ncol0 >= p.N) break;          // warp-uniform: nothing of this slab is inside the matrix
-                    for (int pass = (p.aux ? 0 : 1); pass < 2; ++pass) {
-                        const bool res_staged = (pass == 1) && p.res && p.res_vec && !p.d_fp32;
-                        if (res_staged) {
-                            // coalesced load of the residual slab into the (swizzled) staging buffer
-                            if (lane == 0) bulk_wait_read_prev();
-                            __syncwarp();
-                            const bf16* rbase = p.res + (long long)z1 * p.sr1 + (long long)z0 * p.sr0;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N;
+                const bool use_res = p.res != nullptr;
+                const bf16* const rrow = p.res + r_off;
+                bf16x8 rres[8];
+
+                auto load_res = [&](int sl) {
+                    const int ncol = n_tile * p.block_n + sl * slab_cols;
+                    const int nq = slab_cols / 8;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
-                                const int grow = row0 + rr, gcol = ncol0 + cc * 8;
-                                bf16x8 val;
-                                if (grow < p.M && gcol + 8 <= p.N) {
-                                    val = ld8(rbase + (long long)grow * p.ldr + gcol);
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) val.v[j] = __floats2bfloat162_rn(0.f, 0.f);
-                                    if (grow < p.M)
-                                        for (int j = 0; j < 8; ++j)
-                                            if (gcol + j < p.N)
-                                                reinterpret_cast<bf16*>(&val)[j] = rbase[(long long)grow * p.ldr + gcol + j];
-                                }
-                                *reinterpret_cast<bf16x8*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4)) = val;
-                            }
-                            __syncwarp();
-                        }
-                        for (int ch = 0; ch < chunks; ++ch) {
-                            uint32_t r[32];
-                            const int col0 = sl * slab_cols + ch * 32;
-                            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N + col0, r);
-                            tmem_ld_wait();
-                            const int nbase = n_tile * p.block_n + col0;
-                            float v[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-                            if (p.bias) {
-                                if (nbase + 32 <= p.N) {
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
-                                        v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j)
-                                        if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
-                                }
-                            }
-                            if (pass == 1) {
-                                if (p.act == 1) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                                } else if (p.act == 2) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                                }
-                                if (res_staged) {
-                                    const uint8_t* rowp = stg + lane * 128;
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        float rv[8];
-                                        unpack8(*reinterpret_cast<const bf16x8*>(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4)), rv);
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
-                                    }
-                                } else if (p.res && row_ok) {
-                                    const bf16* rp = p.res + r_off + nbase;
-                                    if (p.res_vec && nbase + 32 <= p.N) {
-#pragma unroll
-                                        for (int q = 0; q < 4; ++q) {
-                                            float rv[8];
-                                            unpack8(ld8(rp + q * 8), rv);
-#pragma unroll
-                                            for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
-                                        }
-                                    } else {
-                                        for (int j = 0; j < 32; ++j)
-                                            if (nbase + j < p.N) v[j] += __bfloat162float(rp[j]);
-                                    }
-                                }
-                            }
-                            if (ch == 0 && !res_staged) {   // this buffer's previous TMA store has read it
-                                if (lane == 0) bulk_wait_read_prev();
-                                __syncwarp();
-                            }
-                            uint8_t* rowp = stg + lane * 128;
-                            if (p.d_fp32) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
-                                        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    for (int q = 0; q < 8; ++q) {
+                        if (q < nq) {
+                            const int n = ncol + q * 8;
+                            if (row_ok && p.res_vec && n + 8 <= p.N) {
+                                rres[q] = ld_nc16(rrow + n);
                             } else {
+                                alignas(16) bf16 t[8];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    *reinterpret_cast<bf16x8*>(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4)) = pack8(v + q * 8);
+                                for (int j = 0; j < 8; ++j)
+                                    t[j] = (row_ok && n + j < p.N) ? rrow[n + j] : __float2bfloat16(0.f);
+                                rres[q] = *reinterpret_cast<const bf16x8*>(t);
                             }
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (pass == 0) tma_store_4d(&map_x, stg, ncol0, row0, z0, z1);
-                            else if (p.atomic) tma_reduce_add_4d(&map_d, stg, ncol0, row0, z0, z1);
-                            else tma_store_4d(&map_d, stg, ncol0, row0, z0, z1);
-                            bulk_commit();
+                    }
+                };
+                // one 32-column chunk: r = raw accumulators of columns [nbase, nbase + 32) of this thread's row
+                auto process = [&](const uint32_t* r, int sl, int ch, int roff) {
+                    const int nbase = n_tile * p.block_n + sl * slab_cols + ch * 32;
+                    float v[32];
+                    if (p.bias) {
+                        if (nbase + 32 <= p.N) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
+                                v[q * 4] = fmaf(__uint_as_float(r[q * 4]), p.alpha, b4.x);
+                                v[q * 4 + 1] = fmaf(__uint_as_float(r[q * 4 + 1]), p.alpha, b4.y);
+                                v[q * 4 + 2] = fmaf(__uint_as_float(r[q * 4 + 2]), p.alpha, b4.z);
+                                v[q * 4 + 3] = fmaf(__uint_as_float(r[q * 4 + 3]), p.alpha, b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (nbase + j < p.N) ? __ldg(p.bias + nbase + j) : 0.f);
                         }
-                        buf = (buf + 1) % EPI_BUFS;
-                        stg = stg0 + buf * STG_BYTES;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                    }
+                    if (ch == 0) {                           // the previous slab's TMA stores have read the staging slabs
+                        if (lane == 0) bulk_wait_read_prev();
+                        __syncwarp();
+                    }
+                    if (p.aux) {                             // pre-activation copy (bf16 outputs only)
+                        const uint32_t rowp = sa_aux;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bf16x8 pk = pack8(v + q * 8);
+                            sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
+                        }
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                    }
+                    if (use_res) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float rv[8];
+                            unpack8(rres[roff + q], rv);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
+                        }
+                    }
+                    const uint32_t rowp = sa_out;
+                    if (p.d_fp32) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) sts16(rowp + ((q ^ (lane & 7)) << 4), v + q * 4);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bf16x8 pk = pack8(v + q * 8);
+                            sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
+                        }
+                    }
+                };
+                auto store_slab = [&](int sl) {
+                    const int ncol0 = n_tile * p.block_n + sl * slab_cols;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.aux) tma_store_4d(&map_x, stg_aux, ncol0, row0, z0, z1);
+                        if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
+                        else tma_store_4d(&map_d, stg_out, ncol0, row0, z0, z1);
+                        bulk_commit();
+                    }
+                };
+                auto slab_ok = [&](int sl) { return sl < n_slabs && n_tile * p.block_n + sl * slab_cols < p.N; };
+
+                uint32_t ra[32], rb[32];
+                int sl = group;
+                if (slab_ok(sl)) {
+                    tmem_ld32(tbase + sl * slab_cols, ra);
+                    if (use_res) load_res(sl);
+                }
+                if (!p.d_fp32) {
+                    while (slab_ok(sl)) {
+                        const bool more = slab_ok(sl + 2);
+                        tmem_ld_wait();
+                        tmem_ld32(tbase + sl * 64 + 32, rb);
+                        process(ra, sl, 0, 0);
+                        tmem_ld_wait();
+                        if (more) tmem_ld32(tbase + (sl + 2) * 64, ra);
+                        process(rb, sl, 1, 4);
+                        if (more && use_res) load_res(sl + 2);
+                        store_slab(sl);
+                        sl += 2;
+                    }
+                } else {
+                    while (slab_ok(sl)) {
+                        bool more = slab_ok(sl + 2);
+                        tmem_ld_wait();
+                        if (more) tmem_ld32(tbase + (sl + 2) * 32, rb);
+                        process(ra, sl, 0, 0);
+                        if (more && use_res) load_res(sl + 2);
+                        store_slab(sl);
+                        sl += 2;
+                        if (!more) break;
+                        more = slab_ok(sl + 2);
+                        tmem_ld_wait();
+                        if (more) tmem_ld32(tbase + (sl + 2) * 32, ra);
+                        process(rb, sl, 0, 0);
+                        if (more && use_res) load_res(sl + 2);
+                        store_slab(sl);
+                        sl += 2;
                     }
                 }
             } else
@@ -681,6 +736,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
                  (a->nb1 == 1 || (a->sd1 * esz) % 16 == 0);
     if (a->aux) d_tma = d_tma && aligned16(a->aux) && !a->d_dtype;
     p.tma_store = d_tma ? 1 : 0;
+    p.stages = (p.tma_store && a->aux) ? 3 : STAGES;     // aux doubles the epilogue staging, paid for with one ring stage
     // bf16 TMA-store slabs are 64 columns wide, so block_n must be a multiple of 64 there
     p.block_n = pick_block_n(a->N, p.b_mn || (d_tma && !a->d_dtype));
     p.m_tiles = dfu_cdiv(a->M, BLOCK_M);

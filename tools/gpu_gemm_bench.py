@@ -87,8 +87,8 @@ def bench_attention(B=128, T=197, H=12, iters=10):
     qkv = (torch.randn(B * T, 3 * H * 64, device=dev) * 0.5).to(torch.bfloat16)
     do = torch.randn(B * T, H * 64, device=dev).to(torch.bfloat16)
     out, P = ops.attention_forward(qkv, B, T, H, 0.125)
-    for name, fn in (("attention fwd (2 bGEMM + softmax)", lambda: ops.attention_forward(qkv, B, T, H, 0.125)),
-                     ("attention bwd (4 bGEMM + softmax)", lambda: ops.attention_backward(qkv, P, do, B, T, H, 0.125))):
+    for name, fn in (("attention fwd (%s)" % ops._ATTN_IMPL, lambda: ops.attention_forward(qkv, B, T, H, 0.125)),
+                     ("attention bwd (%s)" % ops._ATTN_IMPL, lambda: ops.attention_backward(qkv, P, do, B, T, H, 0.125, out=out))):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
