@@ -23,6 +23,8 @@ class GemmArgs(ctypes.Structure):
         ("act", ctypes.c_int32),
         ("impl", ctypes.c_int32),
         ("max_ctas", ctypes.c_int32),
+        ("colstats", ctypes.c_void_p),
+        ("colstats_mode", ctypes.c_int32),
     ]
 
 

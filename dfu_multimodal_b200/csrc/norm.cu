@@ -19,6 +19,7 @@ constexpr int BN_UNROLL = 4;
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z,
                                                         const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ sums, long long M, int C, int relu) {
     __shared__ float red[2][256][9];   // padded against bank conflicts
     const int cvec = C >> 3;
@@ -28,12 +29,16 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-    float mean[8], invstd[8];
+    float mean[8], invstd[8], gsc[8], bsh[8];
+    // relu without a saved output: the mask is recomputed from y (z > 0  <=>  gamma*xhat + beta > 0), one read less
+    const bool mask_from_y = MODE == 1 && relu && z == nullptr;
     if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             mean[i] = mean_invstd[cv * 8 + i];
             invstd[i] = mean_invstd[C + cv * 8 + i];
+            gsc[i] = mask_from_y ? gamma[cv * 8 + i] : 0.f;
+            bsh[i] = mask_from_y ? beta[cv * 8 + i] : 0.f;
         }
     }
     // BN_UNROLL rows per thread per trip: all 128-bit loads are issued before any is consumed (memory-level parallelism)
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
                 va[u] = ld8(a + off);
                 if (MODE == 1) {
                     vy[u] = ld8(y + off);
-                    if (relu) vz[u] = ld8(z + off);
+                    if (relu && !mask_from_y) vz[u] = ld8(z + off);
                 }
             }
         }
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
             } else {
                 float zz[8], yy[8];
                 unpack8(vy[u], yy);
-                if (relu) {
+                if (relu && !mask_from_y) {
                     unpack8(vz[u], zz);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) f[i] = 0.f;
@@ -72,6 +77,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float xh = (yy[i] - mean[i]) * invstd[i];
+                    if (mask_from_y && !(fmaf(gsc[i], xh, bsh[i]) > 0.f)) f[i] = 0.f;
                     s1[i] += f[i];
                     s2[i] += f[i] * xh;
                 }
@@ -170,7 +176,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z,
                                                            const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ sums,
                                                            bf16* __restrict__ dy, bf16* __restrict__ dres,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            long long M, int C, int relu, int train) {
@@ -178,14 +185,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
     const int rows_per_iter = 256 / cvec;
     const int cv = threadIdx.x % cvec;
     const int rl = threadIdx.x / cvec;
-    float mean[8], invstd[8], g[8], k1[8], k2[8];
+    float mean[8], invstd[8], g[8], k1[8], k2[8], gm[8], bt[8];
     const float inv_m = 1.f / (float)M;
+    const bool mask_from_y = relu && z == nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
         mean[i] = mean_invstd[c];
         invstd[i] = mean_invstd[C + c];
         g[i] = gamma[c] * invstd[i];
+        gm[i] = mask_from_y ? gamma[c] : 0.f;
+        bt[i] = mask_from_y ? beta[c] : 0.f;
         k1[i] = train ? sums[c] * inv_m : 0.f;
         k2[i] = train ? sums[C + c] * inv_m : 0.f;
     }
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                 const long long off = r * C + cv * 8;
                 vd[u] = ld8(dz + off);
                 vy[u] = ld8(y + off);
-                if (relu) vz[u] = ld8(z + off);
+                if (relu && !mask_from_y) vz[u] = ld8(z + off);
             }
         }
 #pragma unroll
@@ -217,19 +227,22 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
             float d[8], yy[8];
             unpack8(vd[u], d);
             unpack8(vy[u], yy);
-            if (relu) {
+            if (relu && !mask_from_y) {
                 float zz[8];
                 unpack8(vz[u], zz);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) d[i] = 0.f;
             }
+            float xh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xh[i] = (yy[i] - mean[i]) * invstd[i];
+                if (mask_from_y && !(fmaf(gm[i], xh[i], bt[i]) > 0.f)) d[i] = 0.f;
+            }
             if (dres) st8(dres + off, pack8(d));
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xh = (yy[i] - mean[i]) * invstd[i];
-                o[i] = g[i] * (d[i] - k1[i] - xh * k2[i]);
-            }
+            for (int i = 0; i < 8; ++i) o[i] = g[i] * (d[i] - k1[i] - xh[i] * k2[i]);
             st8(dy + off, pack8(o));
         }
     }
@@ -456,7 +469,7 @@ extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, vo
     DFU_CHECK_ARG(y && sums && M > 0 && bn_shape_ok(C), "dfu_bn_stats: unsupported shape M=%lld C=%d", (long long)M, C);
     const int rpi = 256 / (C / 8);
     bn_reduce_kernel<0><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)y, nullptr, nullptr, nullptr, sums, M, C, 0);
+        (const bf16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
     DFU_CHECK_LAUNCH("bn_stats");
     return DFU_OK;
 }
@@ -485,24 +498,25 @@ extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float
     DFU_CHECK_LAUNCH("bn_apply");
     return DFU_OK;
 }
-extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, float* sums,
-                                 int64_t M, int32_t C, int32_t relu, void* stream) {
-    DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z), "dfu_bn_bwd_reduce: bad args");
+extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+                                 const float* beta, float* sums, int64_t M, int32_t C, int32_t relu, void* stream) {
+    DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z || (gamma && beta)),
+                  "dfu_bn_bwd_reduce: bad args");
     const int rpi = 256 / (C / 8);
     bn_reduce_kernel<1><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, sums, M, C, relu);
+        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu);
     DFU_CHECK_LAUNCH("bn_bwd_reduce");
     return DFU_OK;
 }
 extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
-                                const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int32_t C,
-                                int32_t relu, int32_t train, void* stream) {
-    DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z),
+                                const float* beta, const float* sums, void* dy, void* dres, float* dgamma, float* dbeta,
+                                int64_t M, int32_t C, int32_t relu, int32_t train, void* stream) {
+    DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z || beta),
                   "dfu_bn_bwd_apply: bad args");
     const int rpi = 256 / (C / 8);
     bn_bwd_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta, M,
-        C, relu, train);
+        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta,
+        M, C, relu, train);
     DFU_CHECK_LAUNCH("bn_bwd_apply");
     return DFU_OK;
 }

@@ -55,6 +55,9 @@ struct GemmParams {
     int vec_ok;
     int tma_store;     // epilogue goes through swizzled smem + TMA store / reduce-add
     int stages;        // smem ring depth actually used (<= STAGES)
+    int epi_bufs;      // staging slab sets per epilogue warp (2: the TMA store of slab i overlaps the fill of slab i+1)
+    float* colstats;   // per-column sum (and sum of squares) of D accumulated here when non-null
+    int colstats_mode; // 1: sums[N]; 2: sums[N] then sums of squares[N]
     int res_vec;
 };
 
@@ -143,6 +146,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // the staging slab about to be refilled was handed to TMA EPI_BUFS stores ago
 __device__ __forceinline__ void bulk_wait_read_prev() {
     if (EPI_BUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -175,6 +180,23 @@ __device__ __forceinline__ float gelu_fast(float x) {
     float r;                               // q = inf for large |x| -> r = 0
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
     return fmaf(-0.5f * ax, r, fmaxf(x, 0.f));
+}
+// d/dx gelu(x) = Phi(x) + x phi(x), same erf approximation (Phi = 1 - r/2 for x >= 0, r/2 otherwise).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float q = 0.0000430638f;
+    q = fmaf(q, z, 0.0002765672f);
+    q = fmaf(q, z, 0.0001520143f);
+    q = fmaf(q, z, 0.0092705272f);
+    q = fmaf(q, z, 0.0422820123f);
+    q = fmaf(q, z, 0.0705230784f);
+    q = fmaf(q, z, 1.0f);
+    q = q * q; q = q * q; q = q * q; q = q * q;
+    float r, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+    const float cdf = x >= 0.f ? fmaf(-0.5f, r, 1.f) : 0.5f * r;
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ bf16x8 ld_nc16(const bf16* p) {
     uint4 u;
@@ -223,6 +245,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                      "r"((uint32_t)TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (p.colstats) {        // CTA-wide per-column accumulators, flushed with one global atomic per column at the end
+        float* colacc0 = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
+        for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) colacc0[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -333,9 +359,11 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 // The two warps of a lane quarter alternate slabs; TMA clips rows >= M and columns >= N.  Everything
                 // with latency is issued ahead of its use: the next 32-column TMEM load while the current chunk is in
                 // the FP32 pipes, and the next slab's residual row (8 x 16 B per thread) one slab early.
-                uint8_t* const stg_out = smem + p.stages * STAGE_BYTES + ew * (p.aux ? 2 : 1) * STG_BYTES;
-                uint8_t* const stg_aux = stg_out + STG_BYTES;
-                const uint32_t sa_out = smem_u32(stg_out) + lane * 128, sa_aux = sa_out + STG_BYTES;
+                const int set_bytes = (p.aux ? 2 : 1) * STG_BYTES;          // one staging set: out slab (+ aux slab)
+                uint8_t* const stg_base = smem + p.stages * STAGE_BYTES + ew * p.epi_bufs * set_bytes;
+                const uint32_t sa_base = smem_u32(stg_base) + lane * 128;
+                int bufsel = 0;
+                float* const colacc = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * set_bytes);
                 const int slab_cols = p.d_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
@@ -364,7 +392,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 };
                 // one 32-column chunk: r = raw accumulators of columns [nbase, nbase + 32) of this thread's row
-                auto process = [&](const uint32_t* r, int sl, int ch, int roff) {
+                auto process = [&](uint32_t* r, int sl, int ch, int roff) {
                     const int nbase = n_tile * p.block_n + sl * slab_cols + ch * 32;
                     float v[32];
                     if (p.bias) {
@@ -386,8 +414,11 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
                     }
-                    if (ch == 0) {                           // the previous slab's TMA stores have read the staging slabs
-                        if (lane == 0) bulk_wait_read_prev();
+                    const uint32_t sa_out = sa_base + bufsel * set_bytes, sa_aux = sa_out + STG_BYTES;
+                    if (ch == 0) {                           // the TMA stores that last used this staging set have read it
+                        if (lane == 0) {
+                            if (p.epi_bufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+                        }
                         __syncwarp();
                     }
                     if (p.aux) {                             // pre-activation copy (bf16 outputs only)
@@ -410,8 +441,13 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         for (int q = 0; q < 4; ++q) {
                             float rv[8];
                             unpack8(rres[roff + q], rv);
+                            if (p.act == 3) {                // res holds the pre-activation h: D *= gelu'(h)
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
+                                for (int j = 0; j < 8; ++j) v[q * 8 + j] *= gelu_grad_fast(rv[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
+                            }
                         }
                     }
                     const uint32_t rowp = sa_out;
@@ -425,17 +461,58 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
                         }
                     }
+                    if (p.colstats) {
+                        // column sums of this warp's 32 rows: butterfly reduce-scatter, lane j ends with column j
+                        if (!row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        }
+                        float* sq = reinterpret_cast<float*>(r);        // the raw accumulators are dead by now
+                        if (p.colstats_mode == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                        }
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const bool up = (lane & sft) != 0;
+#pragma unroll
+                            for (int i2 = 0; i2 < sft; ++i2) {
+                                const float send = up ? v[i2] : v[i2 + sft];
+                                const float keep = up ? v[i2 + sft] : v[i2];
+                                v[i2] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                            }
+                        }
+                        if (p.colstats_mode == 2) {
+#pragma unroll
+                            for (int sft = 16; sft >= 1; sft >>= 1) {
+                                const bool up = (lane & sft) != 0;
+#pragma unroll
+                                for (int i2 = 0; i2 < sft; ++i2) {
+                                    const float send = up ? sq[i2] : sq[i2 + sft];
+                                    const float keep = up ? sq[i2 + sft] : sq[i2];
+                                    sq[i2] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                                }
+                            }
+                        }
+                        const int col = nbase + lane;
+                        if (col < p.N) {
+                            atomicAdd(colacc + col, v[0]);
+                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col, sq[0]);
+                        }
+                    }
                 };
                 auto store_slab = [&](int sl) {
                     const int ncol0 = n_tile * p.block_n + sl * slab_cols;
+                    uint8_t* const stg_out = stg_base + bufsel * set_bytes;
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.aux) tma_store_4d(&map_x, stg_aux, ncol0, row0, z0, z1);
+                        if (p.aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
                         if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
                         else tma_store_4d(&map_d, stg_out, ncol0, row0, z0, z1);
                         bulk_commit();
                     }
+                    if (p.epi_bufs == 2) bufsel ^= 1;
                 };
                 auto slab_ok = [&](int sl) { return sl < n_slabs && n_tile * p.block_n + sl * slab_cols < p.N; };
 
@@ -517,14 +594,18 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                     if (p.res) {
                         const bf16* rp = p.res + r_off + n;
+                        float rv[8];
                         if (full8 && p.vec_ok) {
-                            float rv[8];
                             unpack8(ld8(rp), rv);
+                        } else {
+                            for (int j = 0; j < 8; ++j) rv[j] = (n + j < p.N) ? __bfloat162float(rp[j]) : 0.f;
+                        }
+                        if (p.act == 3) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(rv[j]);
+                        } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += rv[j];
-                        } else {
-                            for (int j = 0; j < 8; ++j)
-                                if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
                         }
                     }
                     if (p.d_fp32) {
@@ -573,6 +654,13 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (p.colstats) {
+        const float* colacc0 = reinterpret_cast<const float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
+        for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) {
+            const float sv = colacc0[i];
+            if (sv != 0.f) atomicAdd(p.colstats + i, sv);
+        }
+    }
     if (warp_idx == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -627,7 +715,10 @@ __global__ void __launch_bounds__(256) dfu_ref_gemm_kernel(const RefParams p) {
     if (p.aux) p.aux[d_off] = __float2bfloat16(v);
     if (p.act == 1) v = fmaxf(v, 0.f);
     else if (p.act == 2) v = gelu_erf(v);
-    if (p.res) v += __bfloat162float(p.res[z1 * p.sr1 + z0 * p.sr0 + (long long)m * p.ldr + n]);
+    if (p.res) {
+        const float rv = __bfloat162float(p.res[z1 * p.sr1 + z0 * p.sr0 + (long long)m * p.ldr + n]);
+        if (p.act == 3) v *= gelu_erf_grad(rv); else v += rv;
+    }
     if (p.d_fp32) {
         float* d = reinterpret_cast<float*>(p.D) + d_off;
         if (p.atomic) atomicAdd(d, v); else *d = v;
@@ -699,8 +790,11 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
                   a->M, a->N, a->K);
     DFU_CHECK_ARG(a->A && a->B && a->D, "dfu_gemm: null operand");
     DFU_CHECK_ARG(!(a->accumulate && a->d_dtype != 1), "dfu_gemm: accumulate needs fp32 output");
-    DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias)),
-                  "dfu_gemm: accumulate mode takes no bias/act/res/aux");
+    DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias || a->colstats)),
+                  "dfu_gemm: accumulate mode takes no bias/act/res/aux/colstats");
+    DFU_CHECK_ARG(a->act >= 0 && a->act <= 3 && !(a->act == 3 && !a->res), "dfu_gemm: act=%d (3 needs res = pre-activation)", a->act);
+    DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && a->N <= 2048 && a->nb0 * a->nb1 == 1),
+                  "dfu_gemm: colstats needs mode 1|2, N <= 2048 and no batching");
 
     const bool batched = (a->nb0 * a->nb1) > 1;
     bool tma_ok = aligned16(a->A) && aligned16(a->B) && (a->lda % 8 == 0) && (a->ldb % 8 == 0);
@@ -710,6 +804,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     const bool tiny = a->N < 16;
     int impl = a->impl;
     if (impl == 0 && (!tma_ok || tiny)) impl = 1;   // shape-specialised SIMT kernel, same semantics
+    DFU_CHECK_ARG(!(impl == 1 && a->colstats), "dfu_gemm: colstats is only implemented by the tcgen05 kernel");
 
     if (impl == 1) {
         RefParams p;
@@ -736,7 +831,21 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
                  (a->nb1 == 1 || (a->sd1 * esz) % 16 == 0);
     if (a->aux) d_tma = d_tma && aligned16(a->aux) && !a->d_dtype;
     p.tma_store = d_tma ? 1 : 0;
-    p.stages = (p.tma_store && a->aux) ? 3 : STAGES;     // aux doubles the epilogue staging, paid for with one ring stage
+    // Shared memory plan: 4 ring stages + one staging set per epilogue warp, or 3 stages + 64 KB of staging when the
+    // epilogue needs a second slab (aux) or the per-column accumulators (colstats).
+    p.stages = STAGES;
+    p.epi_bufs = 1;
+    // (measured: a second staging set does not speed up the short-K shapes -- l1 1x1 77 -> 79 us -- and the lost ring
+    // stage slows the K=768 ones, so it is only taken when the third stage is given up anyway)
+    if (p.tma_store && (a->aux || a->colstats)) {
+        p.stages = 3;
+        p.epi_bufs = a->aux ? 1 : 2;     // an aux slab doubles the set size: 3 x 48 KB + 8 x 2 x 4 KB either way
+    }
+    p.colstats = a->colstats; p.colstats_mode = a->colstats_mode;
+    if (a->colstats && !p.tma_store) {
+        dfu_set_error("dfu_gemm: colstats needs a 16-byte aligned output (TMA-store epilogue)");
+        return DFU_ERR_UNSUPPORTED;
+    }
     // bf16 TMA-store slabs are 64 columns wide, so block_n must be a multiple of 64 there
     p.block_n = pick_block_n(a->N, p.b_mn || (d_tma && !a->d_dtype));
     p.m_tiles = dfu_cdiv(a->M, BLOCK_M);

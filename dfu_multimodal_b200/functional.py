@@ -2,11 +2,20 @@
 libdfu_b200.so (through ops.py); autograd supplies the graph bookkeeping so `loss.backward()` and
 `optimizer.step()` behave exactly as they do for the reference's nn.Modules
 (notebooks/train_multimodal_fusion.py:374-380)."""
+import os
+
 import torch
 from torch.autograd import Function
 
 from . import ops
 from .ops import BF16, F32
+
+
+# Epilogue fusions that are implemented and parity-tested but lose on B200 at the benchmark shapes because the GEMMs
+# they attach to are epilogue-bound (small K): measured numbers in profiles/r01e_gemm_bench_isolated.txt.
+FUSE_GELU_BWD = os.environ.get("DFU_FUSE_GELU_BWD", "0") == "1"     # GELU' in the fc2-dgrad epilogue (act=3)
+FUSE_BN_STATS = os.environ.get("DFU_FUSE_BN_STATS", "0") == "1"     # BatchNorm sums in the conv GEMM epilogue (colstats)
+FUSE_SKIP_DGRAD = os.environ.get("DFU_FUSE_SKIP_DGRAD", "0") == "1"  # skip-connection gradient in the conv1 dgrad epilogue
 
 
 def _round8(n):
@@ -109,9 +118,11 @@ class Conv2dFn(Function):
     shapes go through im2col.  Replaces torchvision ResNet's nn.Conv2d (cudnn fwd/dgrad/wgrad)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, pad, fork=False):
+    def forward(ctx, x, weight, stride, pad, fork=False, want_stats=False):
         """fork=True additionally returns x itself (the Bottleneck's skip connection); its gradient is then added
-        in the dgrad GEMM epilogue instead of by a separate pass."""
+        in the dgrad GEMM epilogue instead of by a separate pass.  want_stats=True additionally returns the
+        per-channel sum / sum of squares of the output ([2*Cout] fp32), accumulated by the GEMM epilogue from the fp32
+        accumulators: the BatchNorm that follows needs no statistics pass of its own."""
         xn = ops.as_nhwc(x)
         B, H, W, C = xn.shape
         Cout, Cin, R, S = weight.shape
@@ -123,15 +134,26 @@ class Conv2dFn(Function):
         wm = conv_weight_matrix(weight)
         direct = (R == 1 and S == 1 and stride == 1 and pad == 0 and ldc == Kc)
         A = xn.reshape(B * H * W, C) if direct else ops.im2col(xn, R, S, stride, pad, Ho, Wo, ldc)
-        y, _ = ops.linear_forward(A, wm)
+        sums = None
+        if want_stats and FUSE_BN_STATS and ops.colstats_ok(Cout):
+            sums = ops.zeros(2 * Cout, F32, xn.device)
+        y, _ = ops.linear_forward(A, wm, colstats=sums, colstats_mode=2)
+        if want_stats and sums is None:          # shape the epilogue cannot reduce: separate statistics pass
+            sums = ops.bn_stats(y)
         ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct)
         ctx.save_for_backward(A, weight)
         ctx.fork = fork
-        out = y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
-        return (out, x.view_as(x)) if fork else out
+        out = [y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)]
+        if fork:
+            out.append(x.view_as(x))
+        if want_stats:
+            ctx.mark_non_differentiable(sums)
+            out.append(sums)
+        return tuple(out) if len(out) > 1 else out[0]
 
     @staticmethod
-    def backward(ctx, gy, gskip=None):
+    def backward(ctx, gy, *rest):
+        gskip = rest[0] if ctx.fork else None
         A, weight = ctx.saved_tensors
         B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct = ctx.geom
         g = ops.as_nhwc(gy).reshape(B * Ho * Wo, Cout)
@@ -145,8 +167,12 @@ class Conv2dFn(Function):
         if ctx.needs_input_grad[0]:
             wm = conv_weight_matrix(weight)
             skip = ops.as_nhwc(gskip).reshape(B * H * W, C) if gskip is not None else None
-            if direct:
+            if direct and FUSE_SKIP_DGRAD:
                 dx = ops.linear_dgrad(g, wm, ldc, res=skip).view(B, H, W, C)
+            elif direct:
+                dx = ops.linear_dgrad(g, wm, ldc).view(B, H, W, C)
+                if skip is not None:
+                    dx = ops.add(dx, skip.view(B, H, W, C))
             else:
                 dx = ops.col2im(ops.linear_dgrad(g, wm, ldc), B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
                 if skip is not None:
@@ -154,7 +180,7 @@ class Conv2dFn(Function):
             dx = dx.permute(0, 3, 1, 2)
         elif gskip is not None:
             dx = gskip
-        return dx, dw, None, None, None
+        return dx, dw, None, None, None, None
 
 
 class BatchNormActFn(Function):
@@ -162,26 +188,29 @@ class BatchNormActFn(Function):
     statistics + running-stat update (momentum 0.1, unbiased variance) like torch; eval(): running statistics."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, res, running_mean, running_var, nbt, relu, training, eps, momentum):
+    def forward(ctx, y, gamma, beta, res, running_mean, running_var, nbt, relu, training, eps, momentum, sums=None):
         yn = ops.as_nhwc(y)
         B, H, W, C = yn.shape
         y2 = yn.reshape(B * H * W, C)
         res2 = ops.as_nhwc(res).reshape(B * H * W, C) if res is not None else None
-        z, mi = ops.bn_forward(y2, gamma, beta, running_mean, running_var, nbt, res2, relu, training, eps, momentum)
+        z, mi = ops.bn_forward(y2, gamma, beta, running_mean, running_var, nbt, res2, relu, training, eps, momentum,
+                               sums=sums if training else None)
         ctx.cfg = (B, H, W, C, relu, training, res is not None)
-        ctx.save_for_backward(y2, z if relu else None, mi, gamma)
+        # without a residual input the ReLU mask is recomputed from y in the backward kernels (z is not re-read)
+        ctx.save_for_backward(y2, z if (relu and res is not None) else None, mi, gamma, beta)
         return z.view(B, H, W, C).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gz):
-        y2, z, mi, gamma = ctx.saved_tensors
+        y2, z, mi, gamma, beta = ctx.saved_tensors
         B, H, W, C, relu, training, has_res = ctx.cfg
         g = ops.as_nhwc(gz).reshape(B * H * W, C)
-        dy, dres, dg, db = ops.bn_backward(g, z, y2, mi, gamma, relu, training, has_res and ctx.needs_input_grad[3])
+        dy, dres, dg, db = ops.bn_backward(g, z, y2, mi, gamma, relu, training, has_res and ctx.needs_input_grad[3],
+                                           beta=beta)
         dy = dy.view(B, H, W, C).permute(0, 3, 1, 2)
         if dres is not None:
             dres = dres.view(B, H, W, C).permute(0, 3, 1, 2)
-        return dy, dg, db, dres, None, None, None, None, None, None, None
+        return dy, dg, db, dres, None, None, None, None, None, None, None, None
 
 
 class ReLUFn(Function):
@@ -323,6 +352,48 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_dgrad(g2, shadow(weight, N, K), K).view(ctx.x_shape)
         return dx, dw, db, dres, None, None
+
+
+class MlpFn(Function):
+    """timm Mlp (fc1 -> GELU -> fc2) plus the residual add, as one autograd node.  Forward: GELU and the pre-activation
+    copy come out of the fc1 GEMM epilogue, the residual goes into the fc2 epilogue.  Backward: the GELU derivative is
+    applied in the epilogue of the fc2 dgrad GEMM (act=3) which also accumulates fc1's bias gradient (colstats), so no
+    elementwise pass runs between the five GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, res):
+        Hd, D = w1.shape
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        need_grad = any(ctx.needs_input_grad[:5])
+        a, h = ops.linear_forward(x2, shadow(w1, Hd, D), b1, act=2, want_aux=need_grad)
+        res2 = res.reshape(-1, D) if res is not None else None
+        y, _ = ops.linear_forward(a, shadow(w2, D, Hd), b2, 0, res2)
+        ctx.has_res = res is not None
+        ctx.save_for_backward(x2, w1, w2, h, a)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w1, w2, h, a = ctx.saved_tensors
+        Hd, D = w1.shape
+        g2 = _as_bf16_2d(gy, D)
+        dw2 = ops.linear_wgrad(g2, a, Hd).reshape(w2.shape) if ctx.needs_input_grad[3] else None
+        db2 = ops.colsum(g2) if ctx.needs_input_grad[4] else None
+        if FUSE_GELU_BWD:
+            db1 = ops.zeros(Hd, F32, g2.device) if (ctx.needs_input_grad[2] and ops.colstats_ok(Hd)) else None
+            dh = ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd, res=h, act=3, colstats=db1)
+        else:
+            # measured on B200 (profiles/r01e): the 3072-wide, K=768 dgrad GEMM is epilogue-bound, so GELU' inside
+            # its epilogue (276 us) loses to the plain GEMM (118 us) + one elementwise pass (124 us)
+            db1 = None
+            dh = ops.gelu_bwd(ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd), h)
+        if db1 is None and ctx.needs_input_grad[2]:
+            db1 = ops.colsum(dh)
+        dw1 = ops.linear_wgrad(dh, x2, D).reshape(w1.shape) if ctx.needs_input_grad[1] else None
+        dx = ops.linear_dgrad(dh, shadow(w1, Hd, D), D).view(gy.shape) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, db2, (gy if ctx.has_res else None)
 
 
 class LayerNormFn(Function):

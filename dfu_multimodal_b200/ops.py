@@ -119,7 +119,7 @@ def zeros(shape, dtype, device):
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_off=0, d_off=0, nb0=1, nb1=1,
          sa=(0, 0), sb=(0, 0), sd=(0, 0), accumulate=False, aux=None, bias=None, res=None, ldr=0, sr=(0, 0),
-         r_off=0, alpha=1.0, act=0, impl=None, max_ctas=0):
+         r_off=0, alpha=1.0, act=0, impl=None, max_ctas=0, colstats=None, colstats_mode=0):
     """D[z][m][n] = act(alpha * A.B^T + bias) + res; see dfu_gemm in include/dfu_b200.h. Offsets/strides in elements."""
     _need_cuda(A, B, D, aux, bias, res)
     assert A.dtype == BF16 and B.dtype == BF16 and D.dtype in (BF16, F32)
@@ -136,6 +136,8 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_of
     a.act = act
     a.impl = _GEMM_IMPL if impl is None else impl
     a.max_ctas = max_ctas
+    a.colstats = _p(colstats)
+    a.colstats_mode = colstats_mode if colstats is not None else 0
     if GEMM_EVENTS is not None:
         # bench.py's roofline leg: CUDA events around each GEMM launch, on the launching stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -156,23 +158,31 @@ def _wgrad_needs_splitk(M, N):
     return tiles < 148
 
 
-def linear_forward(x2d, w, bias=None, act=0, res=None, want_aux=False, out_dtype=BF16):
-    """y = act(x2d @ w.T + bias) + res.  x2d [M,K] bf16 (row stride = K), w [N,Kp>=K] bf16 (zero padded)."""
+def colstats_ok(N, out_dtype=BF16):
+    """The GEMM epilogue can accumulate per-column sums when the output rows are 16-byte aligned and N <= 2048."""
+    return N <= 2048 and (N * (2 if out_dtype == BF16 else 4)) % 16 == 0 and N >= 16
+
+
+def linear_forward(x2d, w, bias=None, act=0, res=None, want_aux=False, out_dtype=BF16, colstats=None, colstats_mode=0):
+    """y = act(x2d @ w.T + bias) + res.  x2d [M,K] bf16 (row stride = K), w [N,Kp>=K] bf16 (zero padded).
+    colstats ([N] or [2N] fp32, zeroed) += column sums (and sums of squares, mode 2) of y."""
     M, K = x2d.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=out_dtype, device=x2d.device)
     aux = torch.empty((M, N), dtype=BF16, device=x2d.device) if want_aux else None
     gemm(x2d, w, y, M=M, N=N, K=K, lda=x2d.stride(0), ldb=w.stride(0), ldd=N, bias=bias, act=act, res=res,
-         ldr=(res.stride(0) if res is not None else 0), aux=aux)
+         ldr=(res.stride(0) if res is not None else 0), aux=aux, colstats=colstats, colstats_mode=colstats_mode)
     return y, aux
 
 
-def linear_dgrad(dy2d, w, K, res=None):
-    """dx[M,K] = dy2d[M,N] @ w[N,:K] (+ res)  (w row-major [N, ldw]: MN-major B operand)."""
+def linear_dgrad(dy2d, w, K, res=None, act=0, colstats=None):
+    """dx[M,K] = dy2d[M,N] @ w[N,:K] (+ res)  (w row-major [N, ldw]: MN-major B operand).
+    act=3: dx = (dy2d @ w) * gelu'(res) -- the GELU backward fused into the dgrad epilogue (res = pre-activation);
+    colstats ([K] fp32, zeroed) += column sums of dx (the bias gradient of the layer below)."""
     M, N = dy2d.shape
     dx = torch.empty((M, K), dtype=BF16, device=dy2d.device)
     gemm(dy2d, w, dx, M=M, N=K, K=N, lda=dy2d.stride(0), ldb=w.stride(0), b_major=1, ldd=K, res=res,
-         ldr=(res.stride(0) if res is not None else 0))
+         ldr=(res.stride(0) if res is not None else 0), act=act, colstats=colstats, colstats_mode=1 if colstats is not None else 0)
     return dx
 
 
@@ -300,17 +310,20 @@ def col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc):
 
 
 # ------------------------------------------------------------------------------------------ BatchNorm
-def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, training, eps, momentum):
+def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, training, eps, momentum, sums=None):
+    """`sums` ([2C] fp32: per-channel sum and sum of squares of y) may come from the convolution GEMM's epilogue."""
     M, C = y2d.shape
     dev = y2d.device
     mean_invstd = torch.empty(2 * C, dtype=F32, device=dev)
     L = _L()
     if training:
-        sums = zeros(2 * C, F32, dev)
-        check(L.dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
+        if sums is None:
+            sums = zeros(2 * C, F32, dev)
+            check(L.dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
+            _count()
         check(L.dfu_bn_finalize(_p(sums), _p(mean_invstd), _p(running_mean), _p(running_var), _p(nbt), M, C, eps,
                                 momentum, _st()), "bn_finalize")
-        _count(2)
+        _count()
     else:
         check(L.dfu_bn_eval_stats(_p(running_mean), _p(running_var), _p(mean_invstd), C, eps, _st()), "bn_eval_stats")
         _count()
@@ -321,18 +334,28 @@ def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, tr
     return z, mean_invstd
 
 
-def bn_backward(dz2d, z2d, y2d, mean_invstd, gamma, relu, training, want_dres):
+def bn_stats(y2d):
+    """Per-channel (sum, sum of squares) of y [M, C] -> [2C] fp32."""
+    M, C = y2d.shape
+    sums = zeros(2 * C, F32, y2d.device)
+    check(_L().dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
+    _count()
+    return sums
+
+
+def bn_backward(dz2d, z2d, y2d, mean_invstd, gamma, relu, training, want_dres, beta=None):
+    """z2d may be None for a ReLU block without residual input: the mask is then recomputed from y (needs beta)."""
     M, C = y2d.shape
     dev = y2d.device
     L = _L()
     sums = zeros(2 * C, F32, dev)
-    check(L.dfu_bn_bwd_reduce(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(sums), M, C, 1 if relu else 0, _st()),
-          "bn_bwd_reduce")
+    check(L.dfu_bn_bwd_reduce(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), M, C,
+                              1 if relu else 0, _st()), "bn_bwd_reduce")
     dy = torch.empty_like(y2d)
     dres = torch.empty_like(y2d) if want_dres else None
     dgamma = torch.empty(C, dtype=F32, device=dev)
     dbeta = torch.empty(C, dtype=F32, device=dev)
-    check(L.dfu_bn_bwd_apply(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(gamma), _p(sums), _p(dy), _p(dres),
+    check(L.dfu_bn_bwd_apply(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), _p(dy), _p(dres),
                              _p(dgamma), _p(dbeta), M, C, 1 if relu else 0, 1 if training else 0, _st()),
           "bn_bwd_apply")
     _count(2)

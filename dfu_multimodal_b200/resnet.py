@@ -10,12 +10,16 @@ from .nn import (DfuAvgPoolFlatten, DfuBatchNorm2d, DfuConv2d, DfuLinear, DfuMax
                  has_hooks, to_act)
 
 
-def _bn(y, bn, relu, res=None):
+def _bn(y, bn, relu, res=None, sums=None):
     return Fn.BatchNormActFn.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var,
-                                   bn.num_batches_tracked, relu, bn.training, bn.eps, bn.momentum)
+                                   bn.num_batches_tracked, relu, bn.training, bn.eps, bn.momentum, sums)
 
 
 def _conv_bn(x, conv, bn, relu, res=None):
+    """conv -> BatchNorm (+res) (+ReLU); in train() the batch statistics come out of the conv GEMM's epilogue."""
+    if bn.training:
+        y, sums = Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0], False, True)
+        return _bn(y, bn, relu, res, sums)
     return _bn(Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0]), bn, relu, res)
 
 
@@ -40,8 +44,11 @@ class DfuBottleneck(nn.Module):
             return self._forward_modules(x)
         if torch.is_grad_enabled() and x.requires_grad:
             # conv1 and the skip connection fork here; the skip gradient is added in conv1's dgrad GEMM epilogue
-            y1, xs = Fn.Conv2dFn.apply(x, self.conv1.weight, 1, 0, True)
-            out = _bn(y1, self.bn1, True)
+            if self.bn1.training:
+                y1, xs, sums = Fn.Conv2dFn.apply(x, self.conv1.weight, 1, 0, True, True)
+            else:
+                (y1, xs), sums = Fn.Conv2dFn.apply(x, self.conv1.weight, 1, 0, True), None
+            out = _bn(y1, self.bn1, True, None, sums)
         else:
             xs = x
             out = _conv_bn(x, self.conv1, self.bn1, True)

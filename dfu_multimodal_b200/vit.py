@@ -62,9 +62,10 @@ class DfuMlp(nn.Module):
         self.fc2 = DfuLinear(hidden, dim, std=0.02)
 
     def forward(self, x, res=None):
-        if has_hooks(self.act):
+        if has_hooks(self.act, self.fc1, self.fc2):
             return self.fc2(self.act(self.fc1(x)), res=res)
-        return self.fc2(self.fc1(x, act=2), res=res)      # GELU fused into the fc1 GEMM epilogue
+        # one autograd node: GELU in the fc1 epilogue, residual in the fc2 epilogue, GELU' in the fc2-dgrad epilogue
+        return Fn.MlpFn.apply(to_act(x), self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, res)
 
 
 class DfuBlock(nn.Module):

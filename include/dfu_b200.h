@@ -38,7 +38,11 @@ int dfu_sm_count(void);
  *   z = z1*nb0 + z0, element strides s?0 / s?1 per batch dim.  All strides in ELEMENTS.
  *   d_dtype: 0 = bf16, 1 = fp32.  accumulate=1 (fp32 only): D += result (atomic, enables split-K).
  *   aux (bf16, same geometry as D) receives the pre-activation value when non-null.
- *   act: 0 none, 1 relu, 2 gelu(erf).  impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
+ *   act: 0 none, 1 relu, 2 gelu(erf), 3 = D = (alpha*acc + bias) * gelu'(res) (res holds the pre-activation; fuses the
+ *   GELU backward into the dgrad GEMM).  impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
+ *   colstats (fp32, caller zeroes; tcgen05 kernel only, N <= 2048, unbatched): += per-column sums of D over the M rows
+ *   (mode 1: sums[N]) and sums of squares (mode 2: sums[N], sumsq[N]) -- BatchNorm batch statistics straight from the
+ *   convolution GEMM, bias gradients straight from the dgrad GEMM.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t M, N, K, nb0, nb1;
@@ -53,6 +57,8 @@ typedef struct {
     int32_t act;
     int32_t impl;
     int32_t max_ctas; /* 0 = one per SM */
+    float* colstats;
+    int32_t colstats_mode;
 } dfu_gemm_args;
 int dfu_gemm(const dfu_gemm_args* a, void* stream);
 
@@ -89,14 +95,16 @@ int dfu_bn_eval_stats(const float* running_mean, const float* running_var, float
 /* z = [relu]( gamma*(y-mean)*invstd + beta [+ res] ) */
 int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
                  void* z, int64_t M, int32_t C, int32_t relu, void* stream);
-/* Backward pass 1: sums[0:C] += sum(dpre), sums[C:2C] += sum(dpre*xhat), dpre = dz*(z>0 if relu). */
-int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, float* sums,
-                      int64_t M, int32_t C, int32_t relu, void* stream);
+/* Backward pass 1: sums[0:C] += sum(dpre), sums[C:2C] += sum(dpre*xhat), dpre = dz*(z>0 if relu).
+ * z may be null when the block had no residual input: the mask is then recomputed from y as gamma*xhat+beta > 0
+ * (gamma, beta required), which saves reading z. */
+int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+                      const float* beta, float* sums, int64_t M, int32_t C, int32_t relu, void* stream);
 /* Backward pass 2: dy = gamma*invstd*(dpre - sum_dpre/M - xhat*sum_dpre_xhat/M); dres = dpre (optional);
  * train=0 (eval BN): dy = gamma*invstd*dpre. dgamma/dbeta (fp32 [C]) written when non-null. */
 int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
-                     const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int32_t C,
-                     int32_t relu, int32_t train, void* stream);
+                     const float* beta, const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M,
+                     int32_t C, int32_t relu, int32_t train, void* stream);
 
 /* ------------------------------------ pooling / pointwise ---------------------------------- */
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16; idx (u8, same shape as y, may be null) records the winning tap

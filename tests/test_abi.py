@@ -37,7 +37,7 @@ def test_gemm_args_struct_matches_header_layout():
     # field order of dfu_gemm_args in include/dfu_b200.h
     names = [f[0] for f in _lib.GemmArgs._fields_]
     assert names[:5] == ["M", "N", "K", "nb0", "nb1"]
-    assert names[-4:] == ["alpha", "act", "impl", "max_ctas"]
+    assert names[-6:] == ["alpha", "act", "impl", "max_ctas", "colstats", "colstats_mode"]
     assert ctypes.sizeof(_lib.AdamWTensor) == 48
 
 

@@ -85,6 +85,38 @@ def test_gemm(ops, dev, case, impl):
         close(aux_t, pre, 2 * BF16_EPS, abs_=1e-3)
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K", [(1000, 3072, 768), (333, 200, 96), (64, 64, 64)])
+def test_gemm_gelu_grad_epilogue(ops, dev, M, N, K, impl):
+    """act=3: D = (A B^T) * gelu'(res) -- the GELU backward inside the fc2 dgrad GEMM."""
+    A, B, h = rnd(dev, M, K), rnd(dev, K, N), rnd(dev, M, N, scale=2.0)
+    D = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    ops.gemm(A, B, D, M=M, N=N, K=K, lda=K, ldb=N, ldd=N, b_major=1, res=h, ldr=N, act=3, impl=impl)
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).sum().backward()
+    close(D, (A.float() @ B.float()) * hf.grad, 2 * BF16_EPS, 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,mode,bias", [(5000, 256, 64, 2, 0), (777, 2048, 512, 2, 0), (1000, 3072, 768, 1, 0),
+                                             (300, 64, 147 + 5, 2, 0), (130, 200, 96, 1, 1)])
+def test_gemm_column_statistics_epilogue(ops, dev, M, N, K, mode, bias):
+    """colstats: per-column sum (and sum of squares) of the fp32 results, accumulated by the epilogue."""
+    if not ops.colstats_ok(N):
+        pytest.skip("N outside the epilogue reduction's range")
+    A, B = rnd(dev, M, K), rnd(dev, N, K)
+    bias_t = torch.randn(N, device=dev) if bias else None
+    D = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    st = torch.zeros(N * mode, dtype=torch.float32, device=dev)
+    ops.gemm(A, B, D, M=M, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias_t, colstats=st, colstats_mode=mode)
+    ref = A.float() @ B.float().t()
+    if bias:
+        ref = ref + bias_t
+    close(D, ref, 2 * BF16_EPS, 1e-3)
+    close(st[:N], ref.sum(0), 1e-3, 1e-2 * (M ** 0.5))
+    if mode == 2:
+        close(st[N:], (ref * ref).sum(0), 1e-3, 1e-2 * (M ** 0.5))
+
+
 def test_gemm_alpha_and_padded_leading_dims(ops, dev):
     M, N, K = 197, 197, 64
     A, B = rnd(dev, M, 80), rnd(dev, N, 96)                # lda/ldb larger than K
@@ -204,6 +236,17 @@ def test_batchnorm_train_eval_backward(ops, dev, C, M):
         close(dres, rf.grad, BF16_EPS)
         close(dg, g.grad, 1e-3, 1e-3)
         close(db, b.grad, 1e-3, 1e-3)
+        # ReLU block without residual: the backward kernels recompute the mask from y instead of reading z
+        z3, mi3 = ops.bn_forward(y, gamma, beta, rm.clone(), rv.clone(), nbt.clone(), None, True, True, 1e-5, 0.1)
+        yf3, g3, b3 = y.float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        pre3 = F.batch_norm(yf3, None, None, g3, b3, True, 0.1, 1e-5)
+        (pre3 * (z3.float() > 0)).backward(dz.float())
+        dy3, _, dg3, db3 = ops.bn_backward(dz, None, y, mi3, gamma, True, True, False, beta=beta)
+        dy3z, _, dg3z, db3z = ops.bn_backward(dz, z3, y, mi3, gamma, True, True, False)
+        close(dy3, yf3.grad, 3 * BF16_EPS, 2e-3)
+        close(dg3, g3.grad, 1e-3, 1e-3)
+        close(db3, b3.grad, 1e-3, 1e-3)
+        close(dy3, dy3z, 3 * BF16_EPS, 2e-3)                # mask-from-y agrees with mask-from-z
     rm.normal_(0, 0.1)
     rv.uniform_(0.5, 1.5)
     z2, _ = ops.bn_forward(y, gamma, beta, rm, rv, nbt, None, False, False, 1e-5, 0.1)

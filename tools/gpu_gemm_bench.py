@@ -14,7 +14,7 @@ PEAK = 1638.8
 
 
 def bench(name, M, N, K, a_major=0, b_major=0, fp32=False, acc=False, bias=False, act=0, res=False, aux=False,
-          nb0=1, nb1=1, iters=20):
+          nb0=1, nb1=1, iters=20, colstats=0):
     nb = nb0 * nb1
     A = torch.randn((nb, K, M) if a_major else (nb, M, K), device=dev).to(torch.bfloat16)
     Bm = torch.randn((nb, K, N) if b_major else (nb, N, K), device=dev).to(torch.bfloat16)
@@ -22,6 +22,7 @@ def bench(name, M, N, K, a_major=0, b_major=0, fp32=False, acc=False, bias=False
     bias_t = torch.randn(N, device=dev) if bias else None
     res_t = torch.randn((nb, M, N), device=dev).to(torch.bfloat16) if res else None
     aux_t = torch.empty((nb, M, N), dtype=torch.bfloat16, device=dev) if aux else None
+    cs_t = torch.zeros(N * max(colstats, 1), device=dev) if colstats else None
     lda = M if a_major else K
     ldb = N if b_major else K
 
@@ -29,7 +30,7 @@ def bench(name, M, N, K, a_major=0, b_major=0, fp32=False, acc=False, bias=False
         ops.gemm(A, Bm, D, M=M, N=N, K=K, lda=lda, ldb=ldb, ldd=N, a_major=a_major, b_major=b_major, nb0=nb0, nb1=nb1,
                  sa=(A.stride(0), A.stride(0) * nb0), sb=(Bm.stride(0), Bm.stride(0) * nb0),
                  sd=(M * N, M * N * nb0), bias=bias_t, act=act, res=res_t, ldr=N, sr=(M * N, M * N * nb0), aux=aux_t,
-                 accumulate=acc)
+                 accumulate=acc, colstats=cs_t, colstats_mode=colstats)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -49,6 +50,16 @@ def bench(name, M, N, K, a_major=0, b_major=0, fp32=False, acc=False, bias=False
 
 
 CASES = [
+    ("vit.fc2 dgrad +gelu'", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=3)),
+    ("vit.fc2 dgrad +gelu' +colsum", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=3, colstats=1)),
+    ("vit.fc2 dgrad +colsum", dict(M=25216, N=3072, K=768, b_major=1, colstats=1)),
+    ("l1 1x1 64->256 +bnstats", dict(M=401408, N=256, K=64, colstats=2)),
+    ("l1 1x1 256->64 +bnstats", dict(M=401408, N=64, K=256, colstats=2)),
+    ("l1 3x3 64 (K=576) +bnstats", dict(M=401408, N=64, K=576, colstats=2)),
+    ("l3 1x1 1024->256 +bnstats", dict(M=25088, N=256, K=1024, colstats=2)),
+    ("l4 1x1 512->2048 +bnstats", dict(M=6272, N=2048, K=512, colstats=2)),
+    ("l1 1x1 dgrad 256->64 +res", dict(M=401408, N=256, K=64, b_major=1, res=True)),
+    ("l1 1x1 dgrad 256->64", dict(M=401408, N=256, K=64, b_major=1)),
     # ViT forward
     ("vit.qkv fwd", dict(M=25216, N=2304, K=768, bias=True)),
     ("vit.proj fwd +res", dict(M=25216, N=768, K=768, bias=True, res=True)),
