@@ -124,6 +124,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--vit-sms", type=int, default=0, help="SM budget of the ViT branch stream (0 = whole device)")
+    ap.add_argument("--resnet-sms", type=int, default=0, help="SM budget of the ResNet branch stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -159,7 +161,7 @@ def main():
     torch.manual_seed(0)
     model = D.MultimodalFusionModel(num_classes=2, dropout=0.7).to(dev)
     if not args.no_overlap:
-        model.enable_branch_overlap(True)
+        model.enable_branch_overlap(True, args.vit_sms, args.resnet_sms)
     broadcast_parameters(model)
     opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
     bucketer = None

@@ -13,7 +13,7 @@ void dfu_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int dfu_num_sms() {
+static int physical_sms() {
     static int cached[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -25,9 +25,23 @@ int dfu_num_sms() {
     return cached[dev];
 }
 
+// SM budget of the launches that follow (0 = whole device; process-wide: the host serialises launches): every kernel sizes its grid from dfu_num_sms(), so two
+// streams given complementary budgets share the device side by side (the tensor-bound ViT branch next to the
+// HBM-bound ResNet branch) instead of time-slicing it with full-width launches.
+static volatile int g_sm_budget = 0;
+
+int dfu_num_sms() {
+    const int n = physical_sms();
+    return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+extern "C" int dfu_set_sm_budget(int32_t n_sms) {
+    g_sm_budget = n_sms > 0 ? n_sms : 0;
+    return DFU_OK;
+}
+
 extern "C" const char* dfu_last_error(void) { return g_err; }
 extern "C" int dfu_version(void) { return 100; }
-extern "C" int dfu_sm_count(void) { return dfu_num_sms(); }
+extern "C" int dfu_sm_count(void) { return physical_sms(); }
 
 extern "C" int dfu_device_ok(void) {
     int dev = 0;

@@ -209,6 +209,8 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
+// CS: compile the per-column statistics epilogue in (kept out of the default instantiation: it costs registers).
+template <bool CS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_x,
@@ -246,7 +248,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (p.colstats) {        // CTA-wide per-column accumulators, flushed with one global atomic per column at the end
+    if (CS && p.colstats) {        // CTA-wide per-column accumulators, flushed with one global atomic per column at the end
         float* colacc0 = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
         for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) colacc0[i] = 0.f;
     }
@@ -461,7 +463,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
                         }
                     }
-                    if (p.colstats) {
+                    if (CS && p.colstats) {
                         // column sums of this warp's 32 rows: butterfly reduce-scatter, lane j ends with column j
                         if (!row_ok) {
 #pragma unroll
@@ -654,7 +656,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (p.colstats) {
+    if (CS && p.colstats) {
         const float* colacc0 = reinterpret_cast<const float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
         for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) {
             const float sv = colacc0[i];
@@ -896,7 +898,9 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         }
     }
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
             dfu_set_error("dfu_gemm: cannot reserve %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -905,7 +909,8 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         g_attr_set = true;
     }
     const int grid = (int)min((long long)max_ctas, p.total_work);
-    dfu_tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
+    if (p.colstats) dfu_tc_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
+    else dfu_tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
     return DFU_OK;
 }

@@ -61,25 +61,39 @@ class MultimodalFusionModel(nn.Module):
         self.vit = DfuVisionTransformer(num_classes=0)
         self.fusion = MLPFusion(2048, 768, 512, num_classes, dropout, head_layers)
         self.side_stream = None
+        self.rgb_stream = None
 
     def features(self, rgb, thermal):
-        """Runs the two branches; with `enable_branch_overlap()` they run on two CUDA streams so the HBM-bound
-        ResNet kernels overlap the tensor-core-bound ViT GEMMs."""
-        rgb, thermal = _prep_rgb(rgb), _prep_thermal(thermal)
+        """Runs the two branches; with `enable_branch_overlap()` they run on their own CUDA streams (forward and,
+        through autograd's stream bookkeeping, backward), optionally on complementary SM budgets so the HBM-bound
+        ResNet kernels run beside -- not between -- the tensor-core-bound ViT GEMMs."""
         if self.side_stream is None or not rgb.is_cuda:
+            rgb, thermal = _prep_rgb(rgb), _prep_thermal(thermal)
             return self.resnet.forward_bf16(rgb), self.vit.forward_bf16(thermal)
         main = torch.cuda.current_stream()
-        side = self.side_stream
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            tf = self.vit.forward_bf16(thermal)
-        rf = self.resnet.forward_bf16(rgb)
-        main.wait_stream(side)
+        vs, rs = self.side_stream, self.rgb_stream
+        vs.wait_stream(main)
+        rs.wait_stream(main)
+        with torch.cuda.stream(vs):
+            tf = self.vit.forward_bf16(_prep_thermal(thermal))
+        with torch.cuda.stream(rs):
+            rf = self.resnet.forward_bf16(_prep_rgb(rgb))
+        main.wait_stream(vs)
+        main.wait_stream(rs)
         tf.record_stream(main)
+        rf.record_stream(main)
         return rf, tf
 
-    def enable_branch_overlap(self, enabled=True):
+    def enable_branch_overlap(self, enabled=True, vit_sms=0, resnet_sms=0):
+        """vit_sms / resnet_sms: SM budgets of the two branch streams (0 = each launch spans the whole device)."""
+        if self.side_stream is not None:
+            ops.set_stream_budget(self.side_stream, 0)
+            ops.set_stream_budget(self.rgb_stream, 0)
         self.side_stream = torch.cuda.Stream() if enabled else None
+        self.rgb_stream = torch.cuda.Stream() if enabled else None
+        if enabled:
+            ops.set_stream_budget(self.side_stream, vit_sms)
+            ops.set_stream_budget(self.rgb_stream, resnet_sms)
         return self
 
     def forward(self, rgb, thermal):

@@ -33,8 +33,28 @@ def _L():
     return _lib.load()
 
 
+# stream handle -> SM budget (see dfu_set_sm_budget); empty = every launch sizes itself for the whole device
+_STREAM_BUDGET = {}
+_budget_now = [0]
+
+
+def set_stream_budget(stream, n_sms):
+    """Kernels launched on `stream` size their grids for n_sms SMs (0 / None removes the limit)."""
+    key = stream.cuda_stream
+    if n_sms:
+        _STREAM_BUDGET[key] = int(n_sms)
+    else:
+        _STREAM_BUDGET.pop(key, None)
+
+
 def _st():
-    return torch.cuda.current_stream().cuda_stream
+    s = torch.cuda.current_stream().cuda_stream
+    if _STREAM_BUDGET or _budget_now[0]:
+        want = _STREAM_BUDGET.get(s, 0)
+        if want != _budget_now[0]:
+            _L().dfu_set_sm_budget(want)
+            _budget_now[0] = want
+    return s
 
 
 def _need_cuda(*ts):

@@ -27,6 +27,9 @@ int dfu_version(void);
 /* 0 if the current CUDA device is sm_100 class and the driver TMA entry point resolved. */
 int dfu_device_ok(void);
 int dfu_sm_count(void);
+/* Grid-size budget (in SMs) for the kernels launched next (process-wide); 0 = the whole device.  Lets two streams
+ * run side by side on disjoint SM shares (fusion model: ViT branch next to the ResNet branch). */
+int dfu_set_sm_budget(int32_t n_sms);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM: D[z][m][n] = act(alpha * sum_k A[z][m][k] * B[z][n][k] + bias[n]) + res[z][m][n]
