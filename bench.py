@@ -126,7 +126,11 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--vit-sms", type=int, default=0, help="SM budget of the ViT branch stream (0 = whole device)")
     ap.add_argument("--resnet-sms", type=int, default=0, help="SM budget of the ResNet branch stream")
+    ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks to stderr after this many seconds")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -234,7 +238,7 @@ def main():
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (tcgen05 GEMM)
     roofline = None
-    if rank == 0:
+    if True:     # every rank runs the two eager steps (they contain the gradient all-reduces); rank 0 reports
         peaks = measured_peaks()
         # one eager step with CUDA events around every GEMM launch, on the launching stream
         model.enable_branch_overlap(False)       # serial streams, so each event pair times exactly one launch
