@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z,
                                                            const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ sums,
@@ -399,10 +399,11 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
         }
         __syncthreads();
     }
+    // thread t owns column t: consecutive lanes hit consecutive addresses, so a warp's 32 atomics cover 4 sectors
     for (int t = threadIdx.x; t < D; t += blockDim.x) {
-        const int i = t / nvec, vi = t - i * nvec;
-        atomicAdd(dgamma + vi * 8 + i, sh[t]);
-        atomicAdd(dbeta + vi * 8 + i, sh[D + t]);
+        const int src = (t & 7) * nvec + (t >> 3);
+        atomicAdd(dgamma + t, sh[src]);
+        atomicAdd(dbeta + t, sh[D + src]);
     }
 }
 

@@ -16,24 +16,41 @@ inline int grid_for(long long items, int threads, int per_sm = 8) {
 #define GRID_STRIDE(i, n) \
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
+constexpr int PW_UNROLL = 4;
 // OP: 0 relu, 1 relu_bwd(a=dy, b=y), 2 add, 3 gelu_bwd(a=dy, b=h), 4 gelu
 template <int OP>
 __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                      bf16* __restrict__ out, long long n) {
     const long long nv = n >> 3;
-    GRID_STRIDE(i, nv) {
-        float x[8], y[8], o[8];
-        unpack8(ld8(a + i * 8), x);
-        if (OP != 0 && OP != 4) unpack8(ld8(b + i * 8), y);
+    // PW_UNROLL vectors per thread per trip, all loads issued before the first use
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nv; i0 += stride * PW_UNROLL) {
+        bf16x8 va[PW_UNROLL], vb[PW_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (OP == 0) o[j] = fmaxf(x[j], 0.f);
-            else if (OP == 1) o[j] = (y[j] > 0.f) ? x[j] : 0.f;
-            else if (OP == 2) o[j] = x[j] + y[j];
-            else if (OP == 4) o[j] = gelu_erf(x[j]);
-            else o[j] = x[j] * gelu_erf_grad(y[j]);
+        for (int u = 0; u < PW_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < nv) {
+                va[u] = ld8(a + i * 8);
+                if (OP != 0 && OP != 4) vb[u] = ld8(b + i * 8);
+            }
         }
-        st8(out + i * 8, pack8(o));
+#pragma unroll
+        for (int u = 0; u < PW_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= nv) break;
+            float x[8], y[8], o[8];
+            unpack8(va[u], x);
+            if (OP != 0 && OP != 4) unpack8(vb[u], y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (OP == 0) o[j] = fmaxf(x[j], 0.f);
+                else if (OP == 1) o[j] = (y[j] > 0.f) ? x[j] : 0.f;
+                else if (OP == 2) o[j] = x[j] + y[j];
+                else if (OP == 4) o[j] = gelu_fast(x[j]);
+                else o[j] = x[j] * gelu_grad_fast(y[j]);
+            }
+            st8(out + i * 8, pack8(o));
+        }
     }
     // tail
     if (blockIdx.x == 0) {

@@ -164,40 +164,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// exact-erf GELU through Abramowitz-Stegun 7.1.28 (|erf error| <= 3e-7): one MUFU.RCP and ~14 FP32 ops per element
-// instead of erff(); gelu(x) = relu(x) - 0.5 |x| / (1 + a1 z + ... + a6 z^6)^16 with z = |x| / sqrt(2).
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float ax = fabsf(x);
-    const float z = ax * 0.70710678118654752440f;
-    float q = 0.0000430638f;
-    q = fmaf(q, z, 0.0002765672f);
-    q = fmaf(q, z, 0.0001520143f);
-    q = fmaf(q, z, 0.0092705272f);
-    q = fmaf(q, z, 0.0422820123f);
-    q = fmaf(q, z, 0.0705230784f);
-    q = fmaf(q, z, 1.0f);
-    q = q * q; q = q * q; q = q * q; q = q * q;
-    float r;                               // q = inf for large |x| -> r = 0
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
-    return fmaf(-0.5f * ax, r, fmaxf(x, 0.f));
-}
-// d/dx gelu(x) = Phi(x) + x phi(x), same erf approximation (Phi = 1 - r/2 for x >= 0, r/2 otherwise).
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float q = 0.0000430638f;
-    q = fmaf(q, z, 0.0002765672f);
-    q = fmaf(q, z, 0.0001520143f);
-    q = fmaf(q, z, 0.0092705272f);
-    q = fmaf(q, z, 0.0422820123f);
-    q = fmaf(q, z, 0.0705230784f);
-    q = fmaf(q, z, 1.0f);
-    q = q * q; q = q * q; q = q * q; q = q * q;
-    float r, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
-    const float cdf = x >= 0.f ? fmaf(-0.5f, r, 1.f) : 0.5f * r;
-    return fmaf(x * 0.39894228040143267794f, e, cdf);
-}
 __device__ __forceinline__ bf16x8 ld_nc16(const bf16* p) {
     uint4 u;
     asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
