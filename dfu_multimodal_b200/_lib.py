@@ -28,6 +28,15 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class ConvArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("Cout", ctypes.c_int32), ("R", ctypes.c_int32), ("S", ctypes.c_int32), ("stride", ctypes.c_int32), ("pad", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("ldw", ctypes.c_int64), ("dy", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64), ("accumulate", ctypes.c_int32), ("max_ctas", ctypes.c_int32),
+    ]
+
+
 class AdamWTensor(ctypes.Structure):
     _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("shadow", ctypes.c_void_p), ("numel", ctypes.c_int64)]

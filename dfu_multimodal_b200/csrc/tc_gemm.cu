@@ -56,6 +56,15 @@ struct GemmParams {
     int tma_store;     // epilogue goes through swizzled smem + TMA store / reduce-add
     int stages;        // smem ring depth actually used (<= STAGES)
     int epi_bufs;      // staging slab sets per epilogue warp (2: the TMA store of slab i overlaps the fill of slab i+1)
+    // implicit-GEMM convolution (dfu_conv_gemm): the A (fwd, dgrad) or A and B (wgrad) tiles are gathered by TMA from the
+    // NHWC activation tensor as boxes of pixels shifted by the filter tap; out-of-image pixels read as zero.
+    int cv_mode;              // 0 plain GEMM, 1 forward, 2 dgrad (stride 1), 3 wgrad
+    int cv_wb, cv_hb, cv_bb;  // pixel box of one tile (128 output pixels, or 64 pixels per k-block for wgrad)
+    int cv_tw, cv_th;         // boxes per image row / column
+    int cv_S, cv_pad;         // filter width, padding
+    int cv_cchunks;           // 64-channel chunks of the gathered tensor (fwd: Cin/64, dgrad: Cout/64)
+    int cv_C;                 // channels of the tap-major weight columns (Cin)
+    int cv_sh, cv_sb;         // epilogue slab = 32 tile rows = box (cv_wb, cv_sh, cv_sb)
     float* colstats;   // per-column sum (and sum of squares) of D accumulated here when non-null
     int colstats_mode; // 1: sums[N]; 2: sums[N] then sums of squares[N]
     int res_vec;
@@ -246,13 +255,42 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     uint8_t* sb = sa + A_TILE_BYTES;
                     mbar_expect_tx(&full_bar[stage], stage_tx);
                     const int k0 = kb * BLOCK_K;
-                    if (!p.a_mn) {
+                    if (p.cv_mode == 1 || p.cv_mode == 2) {
+                        // tile = box of output pixels; k-block = (filter tap, 64-channel chunk) of the gathered tensor
+                        const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
+                        const int tap = kb / p.cv_cchunks, cc = kb - tap * p.cv_cchunks;
+                        const int r = tap / p.cv_S, sx = tap - r * p.cv_S;
+                        const int dw = p.cv_mode == 1 ? sx - p.cv_pad : p.cv_pad - sx;
+                        const int dh = p.cv_mode == 1 ? r - p.cv_pad : p.cv_pad - r;
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, wt * p.cv_wb + dw, ht * p.cv_hb + dh, bt * p.cv_bb);
+                        if (p.cv_mode == 1) {
+                            tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, 0, 0);
+                        } else {                         // weights [Cout, (tap, cin)] read as an MN-major operand
+                            for (int j = 0; j < p.block_n / 64; ++j)
+                                tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, tap * p.cv_C + n0 + j * 64, cc * 64, 0, 0);
+                        }
+                    } else if (p.cv_mode == 3) {
+                        // k-block = box of 64 pixels; A = dy (channels contiguous), B = x shifted by the tap of each
+                        // 64-column group of the (tap, cin) output columns
+                        const int wt = kb % p.cv_tw, ht = (kb / p.cv_tw) % p.cv_th, bt = kb / (p.cv_tw * p.cv_th);
+                        const int w0 = wt * p.cv_wb, h0 = ht * p.cv_hb, b0 = bt * p.cv_bb;
+                        tma_load_4d(&map_a, &full_bar[stage], sa, m0, w0, h0, b0);
+                        tma_load_4d(&map_a, &full_bar[stage], sa + 8192, m0 + 64, w0, h0, b0);
+                        for (int j = 0; j < p.block_n / 64; ++j) {
+                            const int ncol = n0 + j * 64;
+                            const int tap = ncol / p.cv_C, c0 = ncol - tap * p.cv_C;
+                            const int r = tap / p.cv_S, sx = tap - r * p.cv_S;
+                            tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, c0, w0 + sx - p.cv_pad, h0 + r - p.cv_pad, b0);
+                        }
+                    } else if (!p.a_mn) {
                         tma_load_4d(&map_a, &full_bar[stage], sa, k0, m0, z0, z1);
                     } else {
                         tma_load_4d(&map_a, &full_bar[stage], sa, m0, k0, z0, z1);
                         tma_load_4d(&map_a, &full_bar[stage], sa + 8192, m0 + 64, k0, z0, z1);
                     }
-                    if (!p.b_mn) {
+                    if (p.cv_mode) {
+                        // B already issued above
+                    } else if (!p.b_mn) {
                         tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, z0, z1);
                     } else {
                         for (int j = 0; j < p.block_n / 64; ++j)
@@ -475,9 +513,17 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
-                        if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
-                        else tma_store_4d(&map_d, stg_out, ncol0, row0, z0, z1);
+                        if (p.cv_mode == 1 || p.cv_mode == 2) {
+                            // this warp's 32 tile rows are the pixel box (cv_wb, cv_sh, cv_sb) of the output image
+                            const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
+                            const int idx0 = quarter * 32;
+                            tma_store_4d(&map_d, stg_out, ncol0, wt * p.cv_wb, ht * p.cv_hb + (idx0 / p.cv_wb) % p.cv_hb,
+                                         bt * p.cv_bb + idx0 / (p.cv_wb * p.cv_hb));
+                        } else {
+                            if (p.aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
+                            if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
+                            else tma_store_4d(&map_d, stg_out, ncol0, row0, z0, z1);
+                        }
                         bulk_commit();
                     }
                     if (p.epi_bufs == 2) bufsel ^= 1;
@@ -733,6 +779,39 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long rows
     return DFU_OK;
 }
 
+// General 4-D bf16/fp32 map: dims/strides in elements (stride[0] is implicit 1), box and traversal strides per dim.
+int make_map_nd(CUtensorMap* map, const void* base, const long long dims_[4], const long long strides_[3], const int box_[4],
+                int esz = 2) {
+    auto enc = get_encode();
+    if (!enc) { dfu_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DFU_ERR_CUDA; }
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) { dims[i] = (cuuint64_t)dims_[i]; box[i] = (cuuint32_t)box_[i]; }
+    for (int i = 0; i < 3; ++i) strides[i] = (cuuint64_t)strides_[i] * esz;
+    CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfu_set_error("cuTensorMapEncodeTiled(4d) failed (%d): dims=%lldx%lldx%lldx%lld box=%dx%dx%dx%d", (int)r, dims_[0], dims_[1],
+                      dims_[2], dims_[3], box_[0], box_[1], box_[2], box_[3]);
+        return DFU_ERR_CUDA;
+    }
+    return DFU_OK;
+}
+
+// Pixel box (wb, hb, bb) with wb*hb*bb == total (powers of two) that wastes the fewest tile rows on a W x H x B image
+// batch; ties go to the widest box (longest contiguous TMA segments).
+void pick_pixel_box(int W, int H, int B, int total, int* wb, int* hb, int* bb) {
+    double best = -1.0;
+    for (int w = 1; w <= 32 && w <= total; w *= 2)
+        for (int h = 1; w * h <= total; h *= 2) {
+            const int b = total / (w * h);
+            const double covered = (double)dfu_cdiv(W, w) * w * dfu_cdiv(H, h) * h * dfu_cdiv(B, b) * b;
+            const double eff = (double)W * H * B / covered + 1e-6 * w + 1e-8 * h;
+            if (eff > best) { best = eff; *wb = w; *hb = h; *bb = b; }
+        }
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int pick_block_n(int N, bool mn_major) {
@@ -791,6 +870,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     }
 
     GemmParams p;
+    memset(&p, 0, sizeof(p));
     p.M = a->M; p.N = a->N; p.K = a->K; p.nb0 = a->nb0; p.nb1 = a->nb1;
     p.a_mn = a->a_major ? 1 : 0;
     p.b_mn = a->b_major ? 1 : 0;
@@ -878,5 +958,131 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     if (p.colstats) dfu_tc_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
     else dfu_tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
+    return DFU_OK;
+}
+
+
+// ----------------------------------------------------------------------------- implicit-GEMM convolution
+extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DFU_CHECK_ARG(a != nullptr, "dfu_conv_gemm: null args");
+    DFU_CHECK_ARG(a->mode >= 1 && a->mode <= 3, "dfu_conv_gemm: mode %d", a->mode);
+    DFU_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->R > 0 && a->S > 0 && a->pad >= 0, "dfu_conv_gemm: bad geometry");
+    if (a->stride != 1 || a->C % 64 != 0 || a->Cout % 64 != 0) {
+        dfu_set_error("dfu_conv_gemm: needs stride 1 and channel counts that are multiples of 64 (C=%d, Cout=%d, stride=%d)",
+                      a->C, a->Cout, a->stride);
+        return DFU_ERR_UNSUPPORTED;
+    }
+    const int Ho = a->H + 2 * a->pad - a->R + 1, Wo = a->W + 2 * a->pad - a->S + 1;
+    DFU_CHECK_ARG(Ho > 0 && Wo > 0, "dfu_conv_gemm: empty output");
+    DFU_CHECK_ARG(a->out && (a->mode == 2 || a->x) && (a->mode == 3 || a->w) && (a->mode == 1 || a->dy),
+                  "dfu_conv_gemm: null operand for mode %d", a->mode);
+    DFU_CHECK_ARG(aligned16(a->out) && aligned16(a->x) && aligned16(a->w) && aligned16(a->dy), "dfu_conv_gemm: unaligned operand");
+    DFU_CHECK_ARG(a->mode == 3 || a->ldw % 8 == 0, "dfu_conv_gemm: weight row stride must be a multiple of 8");
+    DFU_CHECK_ARG(a->mode != 3 || a->ldo % 4 == 0, "dfu_conv_gemm: dW row stride must be a multiple of 4");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.nb0 = p.nb1 = 1;
+    p.alpha = 1.f;
+    p.tma_store = 1;
+    p.stages = STAGES;
+    p.epi_bufs = 1;
+    p.vec_ok = 1;
+    p.cv_mode = a->mode;
+    p.cv_S = a->S;
+    p.cv_pad = a->pad;
+    p.cv_C = a->C;
+    const int taps = a->R * a->S;
+    const int num_sms = dfu_num_sms();
+    const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
+
+    const long long xd[4] = {a->C, a->W, a->H, a->B};
+    const long long xs[3] = {a->C, (long long)a->W * a->C, (long long)a->H * a->W * a->C};
+    const long long yd[4] = {a->Cout, Wo, Ho, a->B};
+    const long long ys[3] = {a->Cout, (long long)Wo * a->Cout, (long long)Ho * Wo * a->Cout};
+    CUtensorMap map_a, map_b, map_d, map_x;
+    memset(&map_x, 0, sizeof(map_x));
+    int rc;
+    if (a->mode == 1 || a->mode == 2) {
+        const bool fwd = a->mode == 1;
+        const int OW = fwd ? Wo : a->W, OH = fwd ? Ho : a->H;            // image the output pixels live in
+        pick_pixel_box(OW, OH, a->B, BLOCK_M, &p.cv_wb, &p.cv_hb, &p.cv_bb);
+        p.cv_tw = dfu_cdiv(OW, p.cv_wb);
+        p.cv_th = dfu_cdiv(OH, p.cv_hb);
+        p.m_tiles = p.cv_tw * p.cv_th * dfu_cdiv(a->B, p.cv_bb);
+        p.M = p.m_tiles * BLOCK_M;
+        p.N = fwd ? a->Cout : a->C;
+        const int gathered_c = fwd ? a->C : a->Cout;
+        p.K = taps * gathered_c;
+        p.cv_cchunks = gathered_c / 64;
+        p.num_kb = taps * p.cv_cchunks;
+        p.a_mn = 0;
+        p.b_mn = fwd ? 0 : 1;
+        p.block_n = pick_block_n(p.N, true);
+        p.n_tiles = dfu_cdiv(p.N, p.block_n);
+        p.split_k = 1;
+        p.kb_per_split = p.num_kb;
+        const int rem = 32 / p.cv_wb;
+        p.cv_sh = p.cv_hb < rem ? p.cv_hb : rem;
+        p.cv_sb = rem / p.cv_sh;
+        const int abox[4] = {64, p.cv_wb, p.cv_hb, p.cv_bb};
+        const int dbox[4] = {64, p.cv_wb, p.cv_sh, p.cv_sb};
+        rc = make_map_nd(&map_a, fwd ? a->x : a->dy, fwd ? xd : yd, fwd ? xs : ys, abox);
+        if (rc) return rc;
+        if (fwd) rc = make_map(&map_b, a->w, p.K, p.N, a->ldw, 1, 0, 1, 0, BLOCK_K, p.block_n);
+        else     rc = make_map(&map_b, a->w, (long long)taps * a->C, a->Cout, a->ldw, 1, 0, 1, 0, 64, BLOCK_K);
+        if (rc) return rc;
+        rc = make_map_nd(&map_d, a->out, fwd ? yd : xd, fwd ? ys : xs, dbox);
+        if (rc) return rc;
+        p.D = a->out;
+        p.d_fp32 = 0;
+    } else {
+        pick_pixel_box(Wo, Ho, a->B, BLOCK_K, &p.cv_wb, &p.cv_hb, &p.cv_bb);
+        p.cv_tw = dfu_cdiv(Wo, p.cv_wb);
+        p.cv_th = dfu_cdiv(Ho, p.cv_hb);
+        p.num_kb = p.cv_tw * p.cv_th * dfu_cdiv(a->B, p.cv_bb);
+        p.M = a->Cout;
+        p.N = taps * a->C;
+        p.K = p.num_kb * BLOCK_K;
+        p.a_mn = p.b_mn = 1;
+        p.block_n = pick_block_n(p.N, true);
+        p.m_tiles = dfu_cdiv(p.M, BLOCK_M);
+        p.n_tiles = dfu_cdiv(p.N, p.block_n);
+        const long long out_tiles = (long long)p.m_tiles * p.n_tiles;
+        int split = 1;
+        if (a->accumulate && out_tiles < max_ctas) {
+            split = (int)((2LL * max_ctas + out_tiles - 1) / out_tiles);
+            split = min(split, max(1, p.num_kb / 4));
+        }
+        p.kb_per_split = dfu_cdiv(p.num_kb, split);
+        p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
+        p.atomic = a->accumulate ? (p.split_k > 1 ? 2 : 1) : 0;
+        const int box[4] = {64, p.cv_wb, p.cv_hb, p.cv_bb};
+        rc = make_map_nd(&map_a, a->dy, yd, ys, box);
+        if (rc) return rc;
+        rc = make_map_nd(&map_b, a->x, xd, xs, box);
+        if (rc) return rc;
+        rc = make_map(&map_d, a->out, p.N, p.M, a->ldo, 1, 0, 1, 0, 32, 32, 4);
+        if (rc) return rc;
+        p.D = a->out;
+        p.ldd = a->ldo;
+        p.d_fp32 = 1;
+    }
+    p.total_work = (long long)p.m_tiles * p.n_tiles * p.split_k;
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            dfu_set_error("dfu_conv_gemm: cannot reserve %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return DFU_ERR_CUDA;
+        }
+        g_attr_set = true;
+    }
+    const int grid = (int)min((long long)max_ctas, p.total_work);
+    dfu_tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
+    DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel(conv)");
     return DFU_OK;
 }

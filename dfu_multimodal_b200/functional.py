@@ -132,6 +132,23 @@ class Conv2dFn(Function):
         Kc = R * S * C
         ldc = _round8(Kc)
         wm = conv_weight_matrix(weight)
+        implicit = ops.conv_implicit_ok(C, Cout, R, S, stride)
+        if implicit:
+            # tiles gathered by TMA straight from the activation tensor: no im2col matrix, x itself is what is saved
+            y = ops.conv_forward(xn, wm, R, S, pad).view(B * Ho * Wo, Cout)
+            sums = ops.bn_stats(y) if want_stats else None
+            ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, False)
+            ctx.implicit = True
+            ctx.save_for_backward(xn, weight)
+            ctx.fork = fork
+            out = [y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)]
+            if fork:
+                out.append(x.view_as(x))
+            if want_stats:
+                ctx.mark_non_differentiable(sums)
+                out.append(sums)
+            return tuple(out) if len(out) > 1 else out[0]
+        ctx.implicit = False
         direct = (R == 1 and S == 1 and stride == 1 and pad == 0 and ldc == Kc)
         A = xn.reshape(B * H * W, C) if direct else ops.im2col(xn, R, S, stride, pad, Ho, Wo, ldc)
         sums = None
@@ -156,6 +173,19 @@ class Conv2dFn(Function):
         gskip = rest[0] if ctx.fork else None
         A, weight = ctx.saved_tensors
         B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, direct = ctx.geom
+        if ctx.implicit:
+            gn = ops.as_nhwc(gy)
+            dw = dx = None
+            if ctx.needs_input_grad[1]:
+                dw = ops.conv_wgrad(gn, A, R, S, pad).reshape(Cout, R, S, C).permute(0, 3, 1, 2)
+            if ctx.needs_input_grad[0]:
+                dx = ops.conv_dgrad(gn, conv_weight_matrix(weight), H, W, C, R, S, pad)
+                if gskip is not None:
+                    dx = ops.add(dx, ops.as_nhwc(gskip))
+                dx = dx.permute(0, 3, 1, 2)
+            elif gskip is not None:
+                dx = gskip
+            return dx, dw, None, None, None, None
         g = ops.as_nhwc(gy).reshape(B * Ho * Wo, Cout)
         dw = None
         if ctx.needs_input_grad[1]:

@@ -7,7 +7,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check
+from ._lib import ConvArgs, GemmArgs, check
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -219,6 +219,66 @@ def linear_wgrad(dy2d, x2d, Kp=None):
     gemm(dy2d, x2d, dw, M=N, N=Kx, K=M, a_major=1, b_major=1, lda=dy2d.stride(0), ldb=x2d.stride(0), ldd=Kx,
          accumulate=acc)
     return dw
+
+
+# ------------------------------------------------------------------------------------------ implicit-GEMM convolution
+_CONV_IMPL = os.environ.get("DFU_CONV_IMPL", "implicit")       # "implicit" (TMA-gathered tiles) | "im2col"
+
+
+def set_conv_impl(impl):
+    global _CONV_IMPL
+    assert impl in ("implicit", "im2col")
+    _CONV_IMPL = impl
+
+
+def conv_implicit_ok(C, Cout, R, S, stride):
+    """Shapes dfu_conv_gemm takes: stride 1, channel counts multiples of 64, a real spatial filter."""
+    return _CONV_IMPL == "implicit" and stride == 1 and R * S > 1 and C % 64 == 0 and Cout % 64 == 0
+
+
+def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False):
+    a = ConvArgs()
+    a.mode, a.B, a.H, a.W, a.C = mode, B, H, W, C
+    a.Cout, a.R, a.S, a.stride, a.pad = Cout, R, S, 1, pad
+    a.x, a.w, a.ldw, a.dy = _p(x), _p(w), (w.stride(0) if w is not None else 0), _p(dy)
+    a.out, a.ldo, a.accumulate, a.max_ctas = _p(out), ldo, 1 if accumulate else 0, 0
+    st = _st()
+    if GEMM_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_L().dfu_conv_gemm(ctypes.byref(a), st), "dfu_conv_gemm")
+        e1.record()
+        GEMM_EVENTS.append((e0, e1, ("conv%d" % mode, B * H * W, Cout, R * S * C, 1, 0, 0, "bf16", 0, 0, 0, 0, 0)))
+    else:
+        check(_L().dfu_conv_gemm(ctypes.byref(a), st), "dfu_conv_gemm")
+    _count()
+    return out
+
+
+def conv_forward(x_nhwc, wm, R, S, pad):
+    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1."""
+    _need_cuda(x_nhwc, wm)
+    B, H, W, C = x_nhwc.shape
+    Cout = wm.shape[0]
+    Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=BF16, device=x_nhwc.device)
+    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y)
+
+
+def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad):
+    B, Ho, Wo, Cout = dy_nhwc.shape
+    dx = torch.empty((B, H, W, C), dtype=BF16, device=dy_nhwc.device)
+    return _conv_call(2, B, H, W, C, Cout, R, S, pad, w=wm, dy=dy_nhwc, out=dx)
+
+
+def conv_wgrad(dy_nhwc, x_nhwc, R, S, pad):
+    """dW [Cout, R*S*C] fp32 (columns ordered (r,s,c))."""
+    B, H, W, C = x_nhwc.shape
+    Cout = dy_nhwc.shape[3]
+    N = R * S * C
+    split = _wgrad_needs_splitk(Cout, N)
+    dw = zeros((Cout, N), F32, x_nhwc.device) if split else torch.empty((Cout, N), dtype=F32, device=x_nhwc.device)
+    return _conv_call(3, B, H, W, C, Cout, R, S, pad, x=x_nhwc, dy=dy_nhwc, out=dw, ldo=N, accumulate=split)
 
 
 # ------------------------------------------------------------------------------------------ layout

@@ -65,6 +65,29 @@ typedef struct {
 } dfu_gemm_args;
 int dfu_gemm(const dfu_gemm_args* a, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on NHWC bf16 (stride 1, channel counts multiples of 64): the same tcgen05 kernel, with the
+ * operand tiles gathered by TMA from the activation tensor as boxes of pixels shifted by the filter tap (padding =
+ * TMA out-of-bounds zero fill).  No im2col / col2im matrix exists.  Replaces cudnn convolution forward / backward
+ * data / backward filter for the 3x3 convolutions of torchvision's Bottleneck (train_multimodal_fusion.py:294).
+ *   mode 1: out = y  [B,Ho,Wo,Cout] bf16  from x [B,H,W,C] and w [Cout, ldw] (columns ordered (r, s, c))
+ *   mode 2: out = dx [B,H,W,C]      bf16  from dy [B,Ho,Wo,Cout] and w
+ *   mode 3: out = dW [Cout, ldo]    fp32  from dy and x; accumulate=1: dW += (caller zeroes; enables split-K)
+ * Returns 3 (unsupported) for other strides / channel counts: the caller then uses dfu_im2col_nhwc + dfu_gemm.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t mode;
+    int32_t B, H, W, C;
+    int32_t Cout, R, S, stride, pad;
+    const void* x;
+    const void* w; int64_t ldw;
+    const void* dy;
+    void* out; int64_t ldo;
+    int32_t accumulate;
+    int32_t max_ctas;
+} dfu_conv_args;
+int dfu_conv_gemm(const dfu_conv_args* a, void* stream);
+
 /* ------------------------------- layout / preprocessing ------------------------------------ */
 /* a9: ToTensor+Normalize (train_multimodal_fusion.py:184-188,201-205) on uint8 HWC images.
  * out NHWC bf16: out[b,h,w,c] = (in/255 - mean[c]) / std[c]. */

@@ -211,6 +211,52 @@ def test_im2col_col2im(ops, dev, C, R, stride, pad, H):
     close(dx.permute(0, 3, 1, 2), F.fold(dunf, (H, H), (R, R), padding=pad, stride=stride), 2 * BF16_EPS, 1e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C,Cout,R,pad", [(2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1),
+                                                (5, 7, 7, 512, 512, 3, 1), (1, 10, 13, 64, 128, 3, 1), (33, 14, 14, 64, 192, 3, 1),
+                                                (2, 9, 9, 128, 64, 5, 2), (2, 12, 12, 64, 64, 3, 0)])
+def test_implicit_gemm_convolution(ops, dev, B, H, W, C, Cout, R, pad):
+    """dfu_conv_gemm (TMA-gathered tiles, no im2col matrix) against torch conv2d forward / input grad / weight grad."""
+    assert ops.conv_implicit_ok(C, Cout, R, R, 1)
+    x = rnd(dev, B, C, H, W)
+    w = rnd(dev, Cout, C, R, R, scale=0.05)
+    xn = x.permute(0, 2, 3, 1).contiguous()                              # NHWC bf16
+    wm = w.permute(0, 2, 3, 1).reshape(Cout, R * R * C).contiguous()     # columns ordered (r, s, c)
+    # float64 CPU reference: cuDNN's fp32 algorithms (TF32, FFT, Winograd) are less exact than fp32 accumulation
+    xf, wf = x.double().cpu().requires_grad_(True), w.double().cpu().requires_grad_(True)
+    ref = F.conv2d(xf, wf, padding=pad)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    y = ops.conv_forward(xn, wm, R, R, pad)
+    assert y.shape == (B, Ho, Wo, Cout)
+    close(y.permute(0, 3, 1, 2), ref, 2 * BF16_EPS, 2e-3)
+    dy = rnd(dev, B, Cout, Ho, Wo)
+    ref.backward(dy.double().cpu())
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dx = ops.conv_dgrad(dyn, wm, H, W, C, R, R, pad)
+    close(dx.permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 2e-3)
+    dw = ops.conv_wgrad(dyn, xn, R, R, pad)
+    close(dw.view(Cout, R, R, C).permute(0, 3, 1, 2), wf.grad, 1e-4, 1e-2)
+
+
+@pytest.mark.parametrize("impl", ["implicit", "im2col"])
+def test_conv_autograd_paths_agree(ops, dev, impl):
+    from dfu_multimodal_b200 import functional as Fn
+    ops.set_conv_impl(impl)
+    try:
+        x = rnd(dev, 2, 64, 14, 14).float().requires_grad_(True)
+        w = (rnd(dev, 128, 64, 3, 3, scale=0.05).float().contiguous(memory_format=torch.channels_last)).requires_grad_(True)
+        y = Fn.Conv2dFn.apply(Fn.ToNHWC.apply(x), w, 1, 1)
+        dy = rnd(dev, 2, 128, 14, 14)
+        y.backward(dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+        xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+        yr = F.conv2d(xr.to(torch.bfloat16).float(), wr.to(torch.bfloat16).float(), padding=1)
+        yr.backward(dy.float())
+        close(y, yr, 2 * BF16_EPS, 2e-3)
+        close(x.grad, xr.grad, 3 * BF16_EPS, 3e-3)
+        close(w.grad, wr.grad, 1e-3, 2e-2)
+    finally:
+        ops.set_conv_impl("implicit")
+
+
 # ----------------------------------------------------------------------------------------------- BatchNorm / LayerNorm
 @pytest.mark.parametrize("C,M", [(64, 5000), (256, 777), (2048, 98), (512, 1)])
 def test_batchnorm_train_eval_backward(ops, dev, C, M):
