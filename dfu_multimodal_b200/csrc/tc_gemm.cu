@@ -185,7 +185,11 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 
 // ----------------------------------------------------------------------------- the kernel
 // CS: compile the per-column statistics epilogue in (kept out of the default instantiation: it costs registers).
-template <bool CS>
+// EM: epilogue specialisation.  The fully general epilogue (EM 0: every feature behind a runtime flag, plus the
+// direct-store path for outputs TMA cannot describe) is ~11k SASS instructions and its warps stall on instruction
+// fetch (ncu: no_inst); the shapes that carry the step get instantiations with the flags folded at compile time:
+//   1 bf16 store   2 bf16 + bias   3 bf16 + bias + residual   4 bf16 + bias + GELU + pre-activation copy   5 fp32 store
+template <bool CS, int EM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_x,
@@ -341,6 +345,14 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else if (warp_idx >= EPI_WARP0) {
         // ---------------------------------------------------------------------- epilogue
         const int ew = warp_idx - EPI_WARP0;
+        constexpr bool GEN = (EM == 0);
+        const bool f_tma = GEN ? (p.tma_store != 0) : true;
+        const bool f_fp32 = GEN ? (p.d_fp32 != 0) : (EM == 5);
+        const bool f_bias = GEN ? (p.bias != nullptr) : (EM >= 2 && EM <= 4);
+        const int f_act = GEN ? p.act : (EM == 4 ? 2 : 0);
+        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3);
+        const bool f_aux = GEN ? (p.aux != nullptr) : (EM == 4);
+        const float alpha = GEN ? p.alpha : 1.f;
         const int quarter = warp_idx & 3;        // TMEM lane quarter this warp may touch
         const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
         const int n_chunks = p.block_n / 32;
@@ -360,21 +372,21 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const bool row_ok = m < p.M;
             const long long d_off = (long long)z1 * p.sd1 + (long long)z0 * p.sd0 + (long long)m * p.ldd;
             const long long r_off = (long long)z1 * p.sr1 + (long long)z0 * p.sr0 + (long long)m * p.ldr;
-            if (p.tma_store) {
+            if (f_tma) {
                 // TMEM -> registers -> bias / act / residual -> swizzled smem slab (32 rows x 128 B) -> TMA store.
                 // The two warps of a lane quarter alternate slabs; TMA clips rows >= M and columns >= N.  Everything
                 // with latency is issued ahead of its use: the next 32-column TMEM load while the current chunk is in
                 // the FP32 pipes, and the next slab's residual row (8 x 16 B per thread) one slab early.
-                const int set_bytes = (p.aux ? 2 : 1) * STG_BYTES;          // one staging set: out slab (+ aux slab)
+                const int set_bytes = (f_aux ? 2 : 1) * STG_BYTES;          // one staging set: out slab (+ aux slab)
                 uint8_t* const stg_base = smem + p.stages * STAGE_BYTES + ew * p.epi_bufs * set_bytes;
                 const uint32_t sa_base = smem_u32(stg_base) + lane * 128;
                 int bufsel = 0;
                 float* const colacc = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * set_bytes);
-                const int slab_cols = p.d_fp32 ? 32 : 64;
+                const int slab_cols = f_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N;
-                const bool use_res = p.res != nullptr;
+                const bool use_res = f_res;
                 const bf16* const rrow = p.res + r_off;
                 bf16x8 rres[8];
 
@@ -401,24 +413,24 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 auto process = [&](uint32_t* r, int sl, int ch, int roff) {
                     const int nbase = n_tile * p.block_n + sl * slab_cols + ch * 32;
                     float v[32];
-                    if (p.bias) {
+                    if (f_bias) {
                         if (nbase + 32 <= p.N) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
-                                v[q * 4] = fmaf(__uint_as_float(r[q * 4]), p.alpha, b4.x);
-                                v[q * 4 + 1] = fmaf(__uint_as_float(r[q * 4 + 1]), p.alpha, b4.y);
-                                v[q * 4 + 2] = fmaf(__uint_as_float(r[q * 4 + 2]), p.alpha, b4.z);
-                                v[q * 4 + 3] = fmaf(__uint_as_float(r[q * 4 + 3]), p.alpha, b4.w);
+                                v[q * 4] = fmaf(__uint_as_float(r[q * 4]), alpha, b4.x);
+                                v[q * 4 + 1] = fmaf(__uint_as_float(r[q * 4 + 1]), alpha, b4.y);
+                                v[q * 4 + 2] = fmaf(__uint_as_float(r[q * 4 + 2]), alpha, b4.z);
+                                v[q * 4 + 3] = fmaf(__uint_as_float(r[q * 4 + 3]), alpha, b4.w);
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (nbase + j < p.N) ? __ldg(p.bias + nbase + j) : 0.f);
+                                v[j] = fmaf(__uint_as_float(r[j]), alpha, (nbase + j < p.N) ? __ldg(p.bias + nbase + j) : 0.f);
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
                     }
                     const uint32_t sa_out = sa_base + bufsel * set_bytes, sa_aux = sa_out + STG_BYTES;
                     if (ch == 0) {                           // the TMA stores that last used this staging set have read it
@@ -427,7 +439,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         }
                         __syncwarp();
                     }
-                    if (p.aux) {                             // pre-activation copy (bf16 outputs only)
+                    if (f_aux) {                             // pre-activation copy (bf16 outputs only)
                         const uint32_t rowp = sa_aux;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -435,10 +447,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
                         }
                     }
-                    if (p.act == 1) {
+                    if (f_act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (p.act == 2) {
+                    } else if (f_act == 2) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
                     }
@@ -447,7 +459,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         for (int q = 0; q < 4; ++q) {
                             float rv[8];
                             unpack8(rres[roff + q], rv);
-                            if (p.act == 3) {                // res holds the pre-activation h: D *= gelu'(h)
+                            if (f_act == 3) {                // res holds the pre-activation h: D *= gelu'(h)
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[q * 8 + j] *= gelu_grad_fast(rv[j]);
                             } else {
@@ -457,7 +469,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         }
                     }
                     const uint32_t rowp = sa_out;
-                    if (p.d_fp32) {
+                    if (f_fp32) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) sts16(rowp + ((q ^ (lane & 7)) << 4), v + q * 4);
                     } else {
@@ -520,7 +532,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             tma_store_4d(&map_d, stg_out, ncol0, wt * p.cv_wb, ht * p.cv_hb + (idx0 / p.cv_wb) % p.cv_hb,
                                          bt * p.cv_bb + idx0 / (p.cv_wb * p.cv_hb));
                         } else {
-                            if (p.aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
+                            if (f_aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
                             if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
                             else tma_store_4d(&map_d, stg_out, ncol0, row0, z0, z1);
                         }
@@ -536,7 +548,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     tmem_ld32(tbase + sl * slab_cols, ra);
                     if (use_res) load_res(sl);
                 }
-                if (!p.d_fp32) {
+                if (!f_fp32) {
                     while (slab_ok(sl)) {
                         const bool more = slab_ok(sl + 2);
                         tmem_ld_wait();
@@ -568,7 +580,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         sl += 2;
                     }
                 }
-            } else
+            } else if (EM == 0)
             for (int c = group; c < n_chunks; c += 2) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * MAX_BLOCK_N + c * 32;
@@ -663,7 +675,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (p.tma_store && lane == 0) bulk_wait0();   // all bulk stores of this warp have completed
+        if (f_tma && lane == 0) bulk_wait0();   // all bulk stores of this warp have completed
     }
 
     tc_fence_before();
@@ -828,6 +840,43 @@ int pick_block_n(int N, bool mn_major) {
 
 bool g_attr_set = false;
 
+cudaError_t set_smem_attrs() {
+    cudaError_t e = cudaSuccess;
+#define DFU_SET_ATTR(CS, EM)                                                                                         \
+    if (e == cudaSuccess)                                                                                            \
+        e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<CS, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
+    DFU_SET_ATTR(true, 0); DFU_SET_ATTR(false, 0); DFU_SET_ATTR(false, 1); DFU_SET_ATTR(false, 2); DFU_SET_ATTR(false, 3);
+    DFU_SET_ATTR(false, 4); DFU_SET_ATTR(false, 5);
+#undef DFU_SET_ATTR
+    return e;
+}
+
+// Which epilogue instantiation serves this launch (-1: the one with the column-statistics code).
+int pick_epilogue_mode(const GemmParams& p) {
+    if (p.colstats) return -1;
+    if (!p.tma_store || p.alpha != 1.f) return 0;
+    const bool bias = p.bias != nullptr, res = p.res != nullptr, aux = p.aux != nullptr;
+    if (p.d_fp32) return (!bias && !res && !aux && p.act == 0) ? 5 : 0;
+    if (!bias && !res && !aux && p.act == 0) return 1;
+    if (bias && !res && !aux && p.act == 0) return 2;
+    if (bias && res && !aux && p.act == 0) return 3;
+    if (bias && !res && aux && p.act == 2) return 4;
+    return 0;
+}
+
+void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                 const CUtensorMap& mx, const GemmParams& p) {
+    switch (em) {
+        case -1: dfu_tc_gemm_kernel<true, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 1: dfu_tc_gemm_kernel<false, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 2: dfu_tc_gemm_kernel<false, 2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 3: dfu_tc_gemm_kernel<false, 3><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 4: dfu_tc_gemm_kernel<false, 4><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 5: dfu_tc_gemm_kernel<false, 5><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        default: dfu_tc_gemm_kernel<false, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+    }
+}
+
 }  // namespace
 
 extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
@@ -944,9 +993,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         }
     }
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = set_smem_attrs();
         if (e != cudaSuccess) {
             dfu_set_error("dfu_gemm: cannot reserve %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -955,8 +1002,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         g_attr_set = true;
     }
     const int grid = (int)min((long long)max_ctas, p.total_work);
-    if (p.colstats) dfu_tc_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
-    else dfu_tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
+    launch_gemm(pick_epilogue_mode(p), grid, stream, map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
     return DFU_OK;
 }
@@ -1071,9 +1117,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     }
     p.total_work = (long long)p.m_tiles * p.n_tiles * p.split_k;
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = set_smem_attrs();
         if (e != cudaSuccess) {
             dfu_set_error("dfu_conv_gemm: cannot reserve %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -1082,7 +1126,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         g_attr_set = true;
     }
     const int grid = (int)min((long long)max_ctas, p.total_work);
-    dfu_tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_d, map_x, p);
+    launch_gemm(pick_epilogue_mode(p), grid, stream, map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel(conv)");
     return DFU_OK;
 }

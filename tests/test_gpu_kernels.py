@@ -247,9 +247,11 @@ def test_conv_autograd_paths_agree(ops, dev, impl):
         y = Fn.Conv2dFn.apply(Fn.ToNHWC.apply(x), w, 1, 1)
         dy = rnd(dev, 2, 128, 14, 14)
         y.backward(dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
-        xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
-        yr = F.conv2d(xr.to(torch.bfloat16).float(), wr.to(torch.bfloat16).float(), padding=1)
-        yr.backward(dy.float())
+        # float64 CPU reference on the bf16-rounded operands (cuDNN fp32 may run TF32 / FFT algorithms)
+        xr = x.detach().to(torch.bfloat16).double().cpu().requires_grad_(True)
+        wr = w.detach().to(torch.bfloat16).double().cpu().contiguous().requires_grad_(True)
+        yr = F.conv2d(xr, wr, padding=1)
+        yr.backward(dy.double().cpu())
         close(y, yr, 2 * BF16_EPS, 2e-3)
         close(x.grad, xr.grad, 3 * BF16_EPS, 3e-3)
         close(w.grad, wr.grad, 1e-3, 2e-2)
