@@ -838,6 +838,22 @@ int pick_block_n(int N, bool mn_major) {
     return best;
 }
 
+// Split-K factor for an accumulating GEMM: minimise (waves of work items) x (k-blocks per item + fixed per-item cost),
+// i.e. account for the wave quantisation of tiles*split over the CTAs instead of just "enough items to fill the GPU".
+int pick_split_k(long long out_tiles, int num_kb, int ctas) {
+    int best = 1;
+    long long best_cost = -1;
+    const int max_split = max(1, min(256, num_kb / 4));
+    for (int sk = 1; sk <= max_split; ++sk) {
+        const int kbs = dfu_cdiv(num_kb, sk);
+        const int real = dfu_cdiv(num_kb, kbs);                 // splits that actually get k-blocks
+        const long long waves = (out_tiles * real + ctas - 1) / ctas;
+        const long long cost = waves * (kbs + 6);                // ~6 k-blocks of pipeline fill + epilogue per item
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sk; }
+    }
+    return best;
+}
+
 bool g_attr_set = false;
 
 cudaError_t set_smem_attrs() {
@@ -952,11 +968,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
     const long long out_tiles = (long long)p.m_tiles * p.n_tiles * a->nb0 * a->nb1;
     int split = 1;
-    if (a->accumulate && out_tiles < max_ctas) {
-        split = (int)((2LL * max_ctas + out_tiles - 1) / out_tiles);
-        // keep at least 4 k-blocks per split so the pipeline amortises its fill
-        split = min(split, max(1, p.num_kb / 4));
-    }
+    if (a->accumulate) split = pick_split_k(out_tiles, p.num_kb, max_ctas);
     p.kb_per_split = dfu_cdiv(p.num_kb, split);
     p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
     p.total_work = out_tiles * p.split_k;
@@ -1097,10 +1109,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.n_tiles = dfu_cdiv(p.N, p.block_n);
         const long long out_tiles = (long long)p.m_tiles * p.n_tiles;
         int split = 1;
-        if (a->accumulate && out_tiles < max_ctas) {
-            split = (int)((2LL * max_ctas + out_tiles - 1) / out_tiles);
-            split = min(split, max(1, p.num_kb / 4));
-        }
+        if (a->accumulate) split = pick_split_k(out_tiles, p.num_kb, max_ctas);
         p.kb_per_split = dfu_cdiv(p.num_kb, split);
         p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
         p.atomic = a->accumulate ? (p.split_k > 1 ? 2 : 1) : 0;
