@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -23,6 +24,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int MAX_BLOCK_N = 256;
+constexpr int MAX_STAGES = 6;         // barrier array size (cta_group::2 runs 6 x 32 KB stages)
 constexpr int STAGES = 4;            // ring depth (3 when a second staging slab per epilogue warp is needed for aux)
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_TILE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KB
@@ -54,7 +56,9 @@ struct GemmParams {
     int act;
     int vec_ok;
     int tma_store;     // epilogue goes through swizzled smem + TMA store / reduce-add
-    int stages;        // smem ring depth actually used (<= STAGES)
+    int stages;        // smem ring depth actually used (<= MAX_STAGES)
+    int cg;            // 1: one CTA per tile; 2: CTA pair per 256-row tile (cta_group::2)
+    int stage_bytes;   // stride of one ring stage (A tile + this CTA's part of the B tile)
     int epi_bufs;      // staging slab sets per epilogue warp (2: the TMA store of slab i overlaps the fill of slab i+1)
     // implicit-GEMM convolution (dfu_conv_gemm): the A (fwd, dgrad) or A and B (wgrad) tiles are gathered by TMA from the
     // NHWC activation tensor as boxes of pixels shifted by the filter tap; out-of-image pixels read as zero.
@@ -162,6 +166,55 @@ __device__ __forceinline__ void bulk_wait_read_prev() {
     if (EPI_BUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
+// ---- cta_group::2 (CTA pair on one 256-row tile): forms taken from CUTLASS cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory, transaction bytes reported to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// MMA completion -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+
 // UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -189,14 +242,17 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 // direct-store path for outputs TMA cannot describe) is ~11k SASS instructions and its warps stall on instruction
 // fetch (ncu: no_inst); the shapes that carry the step get instantiations with the flags folded at compile time:
 //   1 bf16 store   2 bf16 + bias   3 bf16 + bias + residual   4 bf16 + bias + GELU + pre-activation copy   5 fp32 store
-template <bool CS, int EM>
+// CG: 1 = one CTA per 128-row tile; 2 = a CTA pair (cluster of 2) shares a 256-row tile: tcgen05.mma.cta_group::2 issued by
+//     the even CTA, each CTA staging its 128 rows of A and HALF of the B tile, so every SM pulls a third less operand data
+//     per FLOP through its L2 port -- the limit of the 128x256 single-CTA kernel on the K >= 768 shapes.
+template <bool CS, int EM, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_x,
                    const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES];
-    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t full_bar[MAX_STAGES];
+    __shared__ uint64_t empty_bar[MAX_STAGES];
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
@@ -209,56 +265,85 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     }
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
+    const int work0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     if (warp_idx == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS * CG);       // the epilogue warps of both CTAs release the leader
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp_idx == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_slot)),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_slot)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_slot)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (CS && p.colstats) {        // CTA-wide per-column accumulators, flushed with one global atomic per column at the end
-        float* colacc0 = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
+        float* colacc0 = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
         for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) colacc0[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    const uint32_t stage_tx = A_TILE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+    // bytes landing per ring stage: both CTAs' tiles are counted on the leader's barrier
+    const int bn_cta = p.block_n / CG;                              // B-tile rows (N columns) staged by this CTA
+    const uint32_t stage_tx = (uint32_t)CG * (A_TILE_BYTES + (uint32_t)bn_cta * BLOCK_K * 2);
 
     if (warp_idx == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+            for (long long w = work0; w < p.total_work; w += work_step) {
                 long long t = w;
                 const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
                 const int m_tile = (int)(t % p.m_tiles); t /= p.m_tiles;
                 const int ks = (int)(t % p.split_k); t /= p.split_k;
                 const int z0 = (int)(t % p.nb0);
                 const int z1 = (int)(t / p.nb0);
-                const int m0 = m_tile * BLOCK_M, n0 = n_tile * p.block_n;
+                const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M, n0 = n_tile * p.block_n + (int)cta_rank * bn_cta;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], stage_tx);
+                    if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
                     const int k0 = kb * BLOCK_K;
+                    if (CG == 2) {
+                        // each CTA of the pair: its 128 rows of A, its half of the B tile; bytes counted by the leader
+                        if (!p.a_mn) {
+                            tma_load_4d_2sm(&map_a, &full_bar[stage], sa, k0, m0, z0, z1);
+                        } else {
+                            tma_load_4d_2sm(&map_a, &full_bar[stage], sa, m0, k0, z0, z1);
+                            tma_load_4d_2sm(&map_a, &full_bar[stage], sa + 8192, m0 + 64, k0, z0, z1);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_4d_2sm(&map_b, &full_bar[stage], sb, k0, n0, z0, z1);
+                        } else {
+                            for (int j = 0; j < bn_cta / 64; ++j)
+                                tma_load_4d_2sm(&map_b, &full_bar[stage], sb + j * 8192, n0 + j * 64, k0, z0, z1);
+                        }
+                    } else
                     if (p.cv_mode == 1 || p.cv_mode == 2) {
                         // tile = box of output pixels; k-block = (filter tap, 64-channel chunk) of the gathered tensor
                         const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
@@ -292,7 +377,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tma_load_4d(&map_a, &full_bar[stage], sa, m0, k0, z0, z1);
                         tma_load_4d(&map_a, &full_bar[stage], sa + 8192, m0 + 64, k0, z0, z1);
                     }
-                    if (p.cv_mode) {
+                    if (CG == 2 || p.cv_mode) {
                         // B already issued above
                     } else if (!p.b_mn) {
                         tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, z0, z1);
@@ -305,15 +390,15 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0 && cta_rank == 0) {
+            // ------------------------------------------------------------------ MMA issuer (leader CTA only when CG == 2)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) |
                                    ((uint32_t)p.b_mn << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+            for (long long w = work0; w < p.total_work; w += work_step, ++it) {
                 long long t = w / ((long long)p.n_tiles * p.m_tiles);
                 const int ks = (int)(t % p.split_k);
                 const int kb0 = ks * p.kb_per_split;
@@ -326,7 +411,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
                     const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
@@ -334,12 +419,15 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                                                       : make_desc(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = p.b_mn ? make_desc(sb + k * 2048, 8192, 1024)
                                                       : make_desc(sb + k * 32, 16, 1024);
-                        tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CG == 2) tc_mma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
+                    // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+                    if (CG == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs)
+                if (CG == 2) tc_commit_2sm(&tmem_full_bar[acc]); else tc_commit(&tmem_full_bar[acc]);
             }
         }
     } else if (warp_idx >= EPI_WARP0) {
@@ -357,10 +445,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
         const int n_chunks = p.block_n / 32;
         int it = 0;
-        for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+        for (long long w = work0; w < p.total_work; w += work_step, ++it) {
             long long t = w;
             const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
-            const int m_tile = (int)(t % p.m_tiles); t /= p.m_tiles;
+            const int m_tile = (int)(t % p.m_tiles) * CG + (int)cta_rank; t /= p.m_tiles;     // this CTA's 128-row tile
             t /= p.split_k;
             const int z0 = (int)(t % p.nb0);
             const int z1 = (int)(t / p.nb0);
@@ -378,10 +466,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 // with latency is issued ahead of its use: the next 32-column TMEM load while the current chunk is in
                 // the FP32 pipes, and the next slab's residual row (8 x 16 B per thread) one slab early.
                 const int set_bytes = (f_aux ? 2 : 1) * STG_BYTES;          // one staging set: out slab (+ aux slab)
-                uint8_t* const stg_base = smem + p.stages * STAGE_BYTES + ew * p.epi_bufs * set_bytes;
+                uint8_t* const stg_base = smem + p.stages * p.stage_bytes + ew * p.epi_bufs * set_bytes;
                 const uint32_t sa_base = smem_u32(stg_base) + lane * 128;
                 int bufsel = 0;
-                float* const colacc = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * set_bytes);
+                float* const colacc = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * set_bytes);
                 const int slab_cols = f_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
@@ -673,7 +761,9 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cta(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
+            }
         }
         if (f_tma && lane == 0) bulk_wait0();   // all bulk stores of this warp have completed
     }
@@ -681,16 +771,21 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (CS && p.colstats) {
-        const float* colacc0 = reinterpret_cast<const float*>(smem + p.stages * STAGE_BYTES + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
+        const float* colacc0 = reinterpret_cast<const float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * (p.aux ? 2 : 1) * STG_BYTES);
         for (int i = threadIdx.x; i < p.N * p.colstats_mode; i += NUM_THREADS) {
             const float sv = colacc0[i];
             if (sv != 0.f) atomicAdd(p.colstats + i, sv);
         }
     }
+    if (CG == 2) cluster_sync_all();      // neither CTA leaves (or frees TMEM) while its peer may still address it
     if (warp_idx == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                     : "memory");
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -855,14 +950,18 @@ int pick_split_k(long long out_tiles, int num_kb, int ctas) {
 }
 
 bool g_attr_set = false;
+// CTA-pair (cta_group::2) kernel for the large GEMMs; DFU_GEMM_PAIR=0 keeps every launch on the single-CTA kernel
+const bool g_pair_enabled = []() { const char* e = getenv("DFU_GEMM_PAIR"); return !(e && e[0] == '0'); }();
 
 cudaError_t set_smem_attrs() {
     cudaError_t e = cudaSuccess;
-#define DFU_SET_ATTR(CS, EM)                                                                                         \
+#define DFU_SET_ATTR(CS, EM, CG)                                                                                     \
     if (e == cudaSuccess)                                                                                            \
-        e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<CS, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
-    DFU_SET_ATTR(true, 0); DFU_SET_ATTR(false, 0); DFU_SET_ATTR(false, 1); DFU_SET_ATTR(false, 2); DFU_SET_ATTR(false, 3);
-    DFU_SET_ATTR(false, 4); DFU_SET_ATTR(false, 5);
+        e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<CS, EM, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
+    DFU_SET_ATTR(true, 0, 1); DFU_SET_ATTR(false, 0, 1); DFU_SET_ATTR(false, 1, 1); DFU_SET_ATTR(false, 2, 1);
+    DFU_SET_ATTR(false, 3, 1); DFU_SET_ATTR(false, 4, 1); DFU_SET_ATTR(false, 5, 1);
+    DFU_SET_ATTR(false, 1, 2); DFU_SET_ATTR(false, 2, 2); DFU_SET_ATTR(false, 3, 2); DFU_SET_ATTR(false, 4, 2);
+    DFU_SET_ATTR(false, 5, 2);
 #undef DFU_SET_ATTR
     return e;
 }
@@ -880,16 +979,44 @@ int pick_epilogue_mode(const GemmParams& p) {
     return 0;
 }
 
+template <int EM>
+void launch_pair(int grid, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                 const CUtensorMap& mx, const GemmParams& p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, dfu_tc_gemm_kernel<false, EM, 2>, ma, mb, md, mx, p);
+}
+
 void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
                  const CUtensorMap& mx, const GemmParams& p) {
+    if (p.cg == 2) {
+        switch (em) {
+            case 1: launch_pair<1>(grid, stream, ma, mb, md, mx, p); return;
+            case 2: launch_pair<2>(grid, stream, ma, mb, md, mx, p); return;
+            case 3: launch_pair<3>(grid, stream, ma, mb, md, mx, p); return;
+            case 4: launch_pair<4>(grid, stream, ma, mb, md, mx, p); return;
+            default: launch_pair<5>(grid, stream, ma, mb, md, mx, p); return;
+        }
+    }
     switch (em) {
-        case -1: dfu_tc_gemm_kernel<true, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 1: dfu_tc_gemm_kernel<false, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 2: dfu_tc_gemm_kernel<false, 2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 3: dfu_tc_gemm_kernel<false, 3><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 4: dfu_tc_gemm_kernel<false, 4><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 5: dfu_tc_gemm_kernel<false, 5><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        default: dfu_tc_gemm_kernel<false, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case -1: dfu_tc_gemm_kernel<true, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 1: dfu_tc_gemm_kernel<false, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 2: dfu_tc_gemm_kernel<false, 2, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 3: dfu_tc_gemm_kernel<false, 3, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 4: dfu_tc_gemm_kernel<false, 4, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 5: dfu_tc_gemm_kernel<false, 5, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        default: dfu_tc_gemm_kernel<false, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
     }
 }
 
@@ -961,14 +1088,40 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     }
     // bf16 TMA-store slabs are 64 columns wide, so block_n must be a multiple of 64 there
     p.block_n = pick_block_n(a->N, p.b_mn || (d_tma && !a->d_dtype));
-    p.m_tiles = dfu_cdiv(a->M, BLOCK_M);
+    p.stage_bytes = STAGE_BYTES;
+    p.cg = 1;
+    {
+        // CTA-pair kernel for the big unbatched shapes whose N tiles are full 256-wide ones
+        GemmParams probe = p;
+        probe.tma_store = p.tma_store; probe.alpha = a->alpha; probe.bias = a->bias; probe.res = (const bf16*)a->res;
+        probe.aux = (bf16*)a->aux; probe.act = a->act; probe.d_fp32 = a->d_dtype; probe.colstats = a->colstats;
+        const int em = pick_epilogue_mode(probe);
+        if (g_pair_enabled && em >= 1 && !batched && p.block_n == 256 && a->N % 256 == 0 && a->M >= 512 && a->K >= 256 &&
+            a->max_ctas == 0) {
+            // a pair finishes a 256-row tile in ~0.88 of the time two CTAs need for two 128-row tiles (measured), but it
+            // also halves the number of schedulable units: take it only when the wave count does not eat the gain
+            // (split-K launches choose their split for whatever unit count they get)
+            const int ctas = dfu_num_sms();
+            const long long nt = dfu_cdiv(a->N, 256);
+            const long long w1 = (dfu_cdiv(a->M, BLOCK_M) * nt + ctas - 1) / ctas;
+            const long long w2 = (dfu_cdiv(a->M, 2 * BLOCK_M) * nt + ctas / 2 - 1) / (ctas / 2);
+            if (a->accumulate || w2 * 88 < w1 * 100) p.cg = 2;
+        }
+    }
+    if (p.cg == 2) {
+        // per CTA and stage: 128 x 64 of A + 128 x 64 of B = 32 KB -> 6 stages (5 next to the 64 KB aux staging)
+        p.stage_bytes = A_TILE_BYTES + (p.block_n / 2) * BLOCK_K * 2;
+        p.stages = a->aux ? 5 : 6;
+        p.epi_bufs = 1;
+    }
+    p.m_tiles = dfu_cdiv(a->M, BLOCK_M * p.cg);
     p.n_tiles = dfu_cdiv(a->N, p.block_n);
     p.num_kb = dfu_cdiv(a->K, BLOCK_K);
     const int num_sms = dfu_num_sms();
     const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
     const long long out_tiles = (long long)p.m_tiles * p.n_tiles * a->nb0 * a->nb1;
     int split = 1;
-    if (a->accumulate) split = pick_split_k(out_tiles, p.num_kb, max_ctas);
+    if (a->accumulate) split = pick_split_k(out_tiles, p.num_kb, max_ctas / p.cg);
     p.kb_per_split = dfu_cdiv(p.num_kb, split);
     p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
     p.total_work = out_tiles * p.split_k;
@@ -988,7 +1141,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     if (!p.a_mn) rc = make_map(&map_a, a->A, a->K, a->M, a->lda, a->nb0, a->sa0, a->nb1, a->sa1, BLOCK_K, BLOCK_M);
     else         rc = make_map(&map_a, a->A, a->M, a->K, a->lda, a->nb0, a->sa0, a->nb1, a->sa1, 64, BLOCK_K);
     if (rc) return rc;
-    if (!p.b_mn) rc = make_map(&map_b, a->B, a->K, a->N, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, BLOCK_K, p.block_n);
+    if (!p.b_mn) rc = make_map(&map_b, a->B, a->K, a->N, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, BLOCK_K, p.block_n / p.cg);
     else         rc = make_map(&map_b, a->B, a->N, a->K, a->ldb, a->nb0, a->sb0, a->nb1, a->sb1, 64, BLOCK_K);
     if (rc) return rc;
 
@@ -1013,7 +1166,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         }
         g_attr_set = true;
     }
-    const int grid = (int)min((long long)max_ctas, p.total_work);
+    const int grid = p.cg * (int)min((long long)(max_ctas / p.cg), p.total_work);
     launch_gemm(pick_epilogue_mode(p), grid, stream, map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
     return DFU_OK;
@@ -1045,6 +1198,8 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     p.alpha = 1.f;
     p.tma_store = 1;
     p.stages = STAGES;
+    p.stage_bytes = STAGE_BYTES;
+    p.cg = 1;
     p.epi_bufs = 1;
     p.vec_ok = 1;
     p.cv_mode = a->mode;

@@ -51,6 +51,12 @@ GEMM_CASES = [
     (197, 197, 64, 1, 0, 0, 0, 0, 0, 0, 0),
     (1, 768, 768, 0, 0, 1, 0, 0, 0, 0, 0),               # single row (batch-1 inference)
     (4, 2816, 4, 1, 1, 0, 0, 0, 1, 1, 0),                # K smaller than one k-block
+    # shapes the CTA-pair (cta_group::2) kernel takes: M >= 1024, N % 256 == 0, K >= 256
+    (1500, 512, 512, 0, 1, 0, 0, 0, 0, 0, 0),            # dgrad form, ragged M (last 256-row tile is partial)
+    (1024, 768, 3072, 0, 0, 1, 0, 1, 0, 0, 0),           # fc2-like: bias + residual
+    (2304, 768, 4096, 1, 1, 0, 0, 0, 1, 1, 0),           # wgrad form, fp32 split-K reduce-add
+    (1100, 256, 320, 0, 0, 0, 0, 0, 1, 0, 0),            # fp32 store, ragged M and K tail
+    (4096, 1024, 256, 1, 0, 0, 0, 0, 0, 0, 0),           # A MN-major, B K-major
 ]
 
 
