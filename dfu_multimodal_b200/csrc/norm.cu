@@ -17,7 +17,7 @@ constexpr int BN_UNROLL = 4;
 // Thread layout: 256 threads = (256/cvec) row lanes x cvec channel vectors (8 channels each).
 // MODE 0: sums of y and y^2.  MODE 1 (backward): sums of dpre and dpre*xhat.
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z,
+__global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z,
                                                         const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ sums, long long M, int C, int relu) {
@@ -29,16 +29,17 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-    float mean[8], invstd[8], gsc[8], bsh[8];
-    // relu without a saved output: the mask is recomputed from y (z > 0  <=>  gamma*xhat + beta > 0), one read less
+    // xhat = xa*y + xb;  mask (no saved z): mp*y + mq > 0
+    float xa[8], xb[8], mp[8], mq[8];
     const bool mask_from_y = MODE == 1 && relu && z == nullptr;
     if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            mean[i] = mean_invstd[cv * 8 + i];
-            invstd[i] = mean_invstd[C + cv * 8 + i];
-            gsc[i] = mask_from_y ? gamma[cv * 8 + i] : 0.f;
-            bsh[i] = mask_from_y ? beta[cv * 8 + i] : 0.f;
+            const float mean = mean_invstd[cv * 8 + i], invstd = mean_invstd[C + cv * 8 + i];
+            xa[i] = invstd;
+            xb[i] = -mean * invstd;
+            mp[i] = mask_from_y ? gamma[cv * 8 + i] * invstd : 0.f;
+            mq[i] = mask_from_y ? beta[cv * 8 + i] - gamma[cv * 8 + i] * invstd * mean : 1.f;
         }
     }
     // BN_UNROLL rows per thread per trip: all 128-bit loads are issued before any is consumed (memory-level parallelism)
@@ -76,10 +77,9 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const bf16* __restrict__
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float xh = (yy[i] - mean[i]) * invstd[i];
-                    if (mask_from_y && !(fmaf(gsc[i], xh, bsh[i]) > 0.f)) f[i] = 0.f;
+                    if (mask_from_y && !(fmaf(mp[i], yy[i], mq[i]) > 0.f)) f[i] = 0.f;
                     s1[i] += f[i];
-                    s2[i] += f[i] * xh;
+                    s2[i] = fmaf(f[i], fmaf(xa[i], yy[i], xb[i]), s2[i]);
                 }
             }
         }
@@ -175,29 +175,33 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z,
-                                                           const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ sums,
-                                                           bf16* __restrict__ dy, bf16* __restrict__ dres,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           long long M, int C, int relu, int train) {
+                                                              const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ sums,
+                                                              bf16* __restrict__ dy, bf16* __restrict__ dres,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              long long M, int C, int relu, int train) {
     const int cvec = C >> 3;
     const int rows_per_iter = 256 / cvec;
     const int cv = threadIdx.x % cvec;
     const int rl = threadIdx.x / cvec;
-    float mean[8], invstd[8], g[8], k1[8], k2[8], gm[8], bt[8];
+    // Per channel everything is folded into five coefficients (keeps the kernel at 2 blocks/SM without spilling the
+    // in-flight loads):  dy = ca*d + cb*y + cc  with d = dz masked;  mask (no saved z): cp*y + cq > 0.
+    float ca[8], cb[8], cc[8], cp[8], cq[8];
     const float inv_m = 1.f / (float)M;
     const bool mask_from_y = relu && z == nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
-        mean[i] = mean_invstd[c];
-        invstd[i] = mean_invstd[C + c];
-        g[i] = gamma[c] * invstd[i];
-        gm[i] = mask_from_y ? gamma[c] : 0.f;
-        bt[i] = mask_from_y ? beta[c] : 0.f;
-        k1[i] = train ? sums[c] * inv_m : 0.f;
-        k2[i] = train ? sums[C + c] * inv_m : 0.f;
+        const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
+        const float g = gamma[c] * invstd;
+        const float k1 = train ? sums[c] * inv_m : 0.f;
+        const float k2 = train ? sums[C + c] * inv_m : 0.f;
+        ca[i] = g;
+        cb[i] = -g * k2 * invstd;
+        cc[i] = g * (k2 * invstd * mean - k1);
+        cp[i] = mask_from_y ? gamma[c] * invstd : 0.f;
+        cq[i] = mask_from_y ? beta[c] - gamma[c] * invstd * mean : 1.f;
     }
     if (blockIdx.x == 0 && rl == 0 && dgamma) {
 #pragma unroll
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
             dgamma[cv * 8 + i] = sums[C + cv * 8 + i];
         }
     }
+    const bool use_z = relu && !mask_from_y;
     const long long rstride = (long long)gridDim.x * rows_per_iter;
     for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
         bf16x8 vd[BN_UNROLL], vy[BN_UNROLL], vz[BN_UNROLL];
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
                 const long long off = r * C + cv * 8;
                 vd[u] = ld8(dz + off);
                 vy[u] = ld8(y + off);
-                if (relu && !mask_from_y) vz[u] = ld8(z + off);
+                if (use_z) vz[u] = ld8(z + off);
             }
         }
 #pragma unroll
@@ -227,22 +232,19 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
             float d[8], yy[8];
             unpack8(vd[u], d);
             unpack8(vy[u], yy);
-            if (relu && !mask_from_y) {
+            if (use_z) {
                 float zz[8];
                 unpack8(vz[u], zz);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) d[i] = 0.f;
-            }
-            float xh[8];
+            } else if (mask_from_y) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                xh[i] = (yy[i] - mean[i]) * invstd[i];
-                if (mask_from_y && !(fmaf(gm[i], xh[i], bt[i]) > 0.f)) d[i] = 0.f;
+                for (int i = 0; i < 8; ++i) if (!(fmaf(cp[i], yy[i], cq[i]) > 0.f)) d[i] = 0.f;
             }
             if (dres) st8(dres + off, pack8(d));
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = g[i] * (d[i] - k1[i] - xh[i] * k2[i]);
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(ca[i], d[i], fmaf(cb[i], yy[i], cc[i]));
             st8(dy + off, pack8(o));
         }
     }
