@@ -14,6 +14,7 @@
 //
 // Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 softmax /
 // epilogue (warp w owns TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter split the columns).
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "../../include/dfu_b200.h"
 
@@ -484,7 +485,264 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward, pipelined
+// Same mathematics as attn_bwd_kernel, cut into 2 key tiles x 4 query chunks of 64 (64, 64, 64, 16) so that the tensor
+// core and the exp / dS warps overlap: S^T / dP^T of chunk c+1 are issued before the warps have finished chunk c (two
+// TMEM buffers of 2 x 64 columns), the P^T / dS^T operand tiles are double-buffered in shared memory, dV / dK accumulate
+// per chunk and dQ per chunk PAIR (M = 128 queries, the two dS^T buffers read as one MN-major operand).
+constexpr int P_PT0 = 4 * KV_BYTES, P_DST0 = P_PT0 + 2 * TILE128_BYTES;      // PT[2] then DST[2], 16 KB each
+constexpr int P_SD = 0;                                                      // TMEM: buffer b -> S^T at b*128, dP^T at b*128+64
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                     bf16* __restrict__ dqkv, int B, int T, int H, float scale) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float lse2_s[KV_ROWS], dsum_s[KV_ROWS];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NK = (T + 15) & ~15;
+    const int items = B * H;
+    const int D3 = 3 * H * HD;
+
+    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_qkv); prefetch_tmap(&map_do); }
+    if (warp_idx == 1 && lane == 0) {
+        mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&sd_full[b], 1); mbar_init(&tile_full[b], 16); mbar_init(&tile_free[b], 1); }
+        mbar_init(&acc_full, 1); mbar_init(&acc_empty, 16); mbar_init(&dq_full, 1); mbar_init(&dq_empty, 16);
+        fence_mbar_init();
+    }
+    if (warp_idx == 2) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+                const int b = w / H, h = w - b * H;
+                const int row0 = b * T;
+                mbar_wait(&ops_empty, (it & 1) ^ 1);
+                mbar_expect_tx(&ops_full, 4 * KV_BYTES);
+                tma_load_2d(&map_qkv, &ops_full, smem + B_Q, h * HD, row0);
+                tma_load_2d(&map_qkv, &ops_full, smem + B_K, (H + h) * HD, row0);
+                tma_load_2d(&map_qkv, &ops_full, smem + B_V, (2 * H + h) * HD, row0);
+                tma_load_2d(&map_do, &ops_full, smem + B_DO, h * HD, row0);
+                if (w + (int)gridDim.x < items) {
+                    const int wn = w + gridDim.x, bn = wn / H, hn = wn - bn * H;
+                    tma_prefetch_2d(&map_qkv, hn * HD, bn * T);
+                    tma_prefetch_2d(&map_qkv, (H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&map_qkv, (2 * H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&map_do, hn * HD, bn * T);
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            const uint32_t sQ = smem_u32(smem + B_Q), sK = smem_u32(smem + B_K), sV = smem_u32(smem + B_V),
+                           sDO = smem_u32(smem + B_DO), sPT = smem_u32(smem + P_PT0), sDST = smem_u32(smem + P_DST0);
+            const uint32_t idesc_acc = make_idesc(128, HD, 0, 1);      // dV, dK: A K-major, B MN-major
+            const uint32_t idesc_dq = make_idesc(128, HD, 1, 1);       // dQ: A (dS^T buffers) MN-major, B MN-major
+            const uint32_t idesc_s64 = make_idesc(128, 64, 0, 0), idesc_s16 = make_idesc(128, 16, 0, 0);
+            // S^T = K_kt Q_qc^T and dP^T = V_kt dO_qc^T of chunk (kt, qc) into TMEM buffer qc & 1
+            auto issue_sd = [&](int kt, int qc) {
+                const uint32_t tb = tmem + P_SD + (qc & 1) * 128;
+                const uint32_t id = qc == 3 ? idesc_s16 : idesc_s64;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    tc_mma_f16(tb, make_desc(sK + kt * TILE128_BYTES + k * 32, 16, 1024),
+                               make_desc(sQ + qc * 8192 + k * 32, 16, 1024), id, k > 0);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    tc_mma_f16(tb + 64, make_desc(sV + kt * TILE128_BYTES + k * 32, 16, 1024),
+                               make_desc(sDO + qc * 8192 + k * 32, 16, 1024), id, k > 0);
+                tc_commit(&sd_full[qc & 1]);
+            };
+            int it = 0;
+            uint32_t use[2] = {0, 0};      // completed uses of each buffer (phase of tile_full)
+            uint32_t ktg = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+                mbar_wait(&ops_full, it & 1);
+                mbar_wait(&dq_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                issue_sd(0, 0);
+                for (int kt = 0; kt < 2; ++kt, ++ktg) {
+                    const int key_steps = (kt == 0 ? 128 : NK - 128) / 16;
+                    for (int qc = 0; qc < 4; ++qc) {
+                        const int b = qc & 1;
+                        // next chunk's S^T / dP^T: its TMEM buffer was read out before tile_full of the step two back
+                        if (qc < 3) issue_sd(kt, qc + 1);
+                        else if (kt == 0) issue_sd(1, 0);
+                        mbar_wait(&tile_full[b], use[b] & 1);
+                        ++use[b];
+                        tc_fence_after();
+                        if (qc == 0) {
+                            mbar_wait(&acc_empty, (ktg & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        const int q_steps = qc == 3 ? 1 : 4;
+                        for (int k = 0; k < q_steps; ++k) {
+                            const uint64_t bdo = make_desc(sDO + qc * 8192 + k * 2048, 8192, 1024);
+                            const uint64_t bq = make_desc(sQ + qc * 8192 + k * 2048, 8192, 1024);
+                            tc_mma_f16(tmem + C_DV, make_desc(sPT + b * TILE128_BYTES + k * 32, 16, 1024), bdo, idesc_acc,
+                                       (qc > 0 || k > 0));
+                            tc_mma_f16(tmem + C_DK, make_desc(sDST + b * TILE128_BYTES + k * 32, 16, 1024), bq, idesc_acc,
+                                       (qc > 0 || k > 0));
+                        }
+                        if (b == 1) {
+                            // dQ of the query tile this pair of chunks covers: the two dS^T buffers as one MN-major operand
+                            for (int k = 0; k < key_steps; ++k)
+                                tc_mma_f16(tmem + C_DQ + (qc >> 1) * HD, make_desc(sDST + k * 2048, TILE128_BYTES, 1024),
+                                           make_desc(sK + kt * TILE128_BYTES + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0));
+                            tc_commit(&tile_free[0]);
+                            tc_commit(&tile_free[1]);
+                        }
+                    }
+                    tc_commit(&acc_full);
+                }
+                tc_commit(&dq_full);
+                tc_commit(&ops_empty);
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // 16 warps: warp (quarter, cg) owns TMEM lanes 32*quarter..+31 and 16 of the 64 query columns of each chunk
+        const int ew = warp_idx - 4;
+        const int cg = ew >> 2;
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const int ct = threadIdx.x - 128;
+        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = scale * LOG2E;
+        const uint32_t sPT = smem_u32(smem + P_PT0) + row * 128;
+        const uint32_t sDST = smem_u32(smem + P_DST0) + row * 128;
+        int it = 0;
+        uint32_t use[2] = {0, 0};
+        uint32_t ktg = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            const int b = w / H, h = w - b * H;
+            named_bar_sync(1, 512);
+            if (ct < KV_ROWS) {
+                float d = 0.f, l2 = 0.f;
+                if (ct < T) {
+                    const long long off = ((long long)b * T + ct) * (H * HD) + h * HD;
+                    bf16x8 vo[8], vg[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { vo[k] = ld_global_v4(out + off + k * 8); vg[k] = ld_global_v4(dout + off + k * 8); }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float fo[8], fg[8];
+                        unpack8(vo[k], fo);
+                        unpack8(vg[k], fg);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) d += fo[j] * fg[j];
+                    }
+                    l2 = lse[((long long)b * H + h) * T + ct] * LOG2E;
+                }
+                dsum_s[ct] = d;
+                lse2_s[ct] = l2;
+            }
+            named_bar_sync(1, 512);
+            for (int kt = 0; kt < 2; ++kt, ++ktg) {
+                const int key = kt * 128 + row;
+                const bool key_ok = key < T;
+                for (int qc = 0; qc < 4; ++qc) {
+                    const int bf = qc & 1;
+                    mbar_wait(&sd_full[bf], use[bf] & 1);
+                    tc_fence_after();
+                    const bool active = qc < 3 || cg == 0;        // the last chunk holds 16 queries
+                    float p[16], ds[16];
+                    if (active) {
+                        uint32_t s[16], dp[16];
+                        tmem_ld16(tlane + P_SD + bf * 128 + cg * 16, s);
+                        tmem_ld16(tlane + P_SD + bf * 128 + 64 + cg * 16, dp);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int q = qc * 64 + cg * 16 + j;
+                            const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lse2_s[q]);
+                            const bool ok = key_ok && (q < T);
+                            p[j] = ok ? e : 0.f;
+                            ds[j] = ok ? e * (__uint_as_float(dp[j]) - dsum_s[q]) * scale : 0.f;
+                        }
+                    }
+                    // the MMAs of the pair that last used this smem buffer have finished reading it
+                    mbar_wait(&tile_free[bf], (use[bf] & 1) ^ 1);
+                    ++use[bf];
+                    if (active) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t off = bf * TILE128_BYTES + (((cg * 2 + j) ^ (row & 7)) << 4);
+                            st_shared_v4(sPT + off, pack8(p + j * 8));
+                            st_shared_v4(sDST + off, pack8(ds + j * 8));
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tile_full[bf]);
+                }
+                mbar_wait(&acc_full, ktg & 1);
+                tc_fence_after();
+                {
+                    const int which = cg >> 1, half = cg & 1;      // which: 0 = dV, 1 = dK
+                    bf16* drow = dqkv + ((long long)b * T + key) * D3 + (which == 0 ? 2 * H : H) * HD + h * HD + half * 32;
+                    uint32_t r[32];
+                    tmem_ld32(tlane + (which == 0 ? C_DV : C_DK) + half * 32, r);
+                    tmem_ld_wait();
+                    if (key_ok) {
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
+                            st_global_v4(drow + gq * 8, pack8(v));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty);
+            }
+            mbar_wait(&dq_full, it & 1);
+            tc_fence_after();
+            {
+                const int qt = cg >> 1, half = cg & 1;
+                const int q = qt * 128 + row;
+                bf16* drow = dqkv + ((long long)b * T + q) * D3 + h * HD + half * 32;
+                uint32_t r[32];
+                tmem_ld32(tlane + C_DQ + qt * HD + half * 32, r);
+                tmem_ld_wait();
+                if (q < T) {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
+                        st_global_v4(drow + gq * 8, pack8(v));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dq_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 bool g_attr_fwd = false, g_attr_bwd = false;
+// DFU_ATTN_BWD=serial selects the unpipelined backward kernel
+const bool g_bwd_pipe = []() { const char* e = getenv("DFU_ATTN_BWD"); return !(e && e[0] == 's'); }();
 
 int check_shape(const char* what, int B, int T, int H) {
     DFU_CHECK_ARG(B > 0 && H > 0 && T > 128 && T <= KV_ROWS, "%s: supports 128 < T <= %d tokens (got T=%d, B=%d, H=%d)", what,
@@ -532,6 +790,8 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     if (int rc = make_map_2d(&map_do, dout, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;
     if (!g_attr_bwd) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
         if (e != cudaSuccess) {
             dfu_set_error("dfu_attention_bwd: cannot reserve %d B shared memory: %s", BWD_SMEM, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -541,8 +801,12 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     }
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
-    attn_bwd_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
-                                                                       lse, (bf16*)dqkv, B, T, H, scale);
+    if (g_bwd_pipe)
+        attn_bwd_pipe_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(map_qkv, map_do, (const bf16*)out,
+                                                                                (const bf16*)dout, lse, (bf16*)dqkv, B, T, H, scale);
+    else
+        attn_bwd_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
+                                                                           lse, (bf16*)dqkv, B, T, H, scale);
     DFU_CHECK_LAUNCH("attn_bwd_kernel");
     return DFU_OK;
 }
