@@ -166,7 +166,7 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_major=0, b_major=0, a_off=0, b_of
         e1.record()
         GEMM_EVENTS.append((e0, e1, (M, N, K, nb0 * nb1, a_major, b_major, "f32" if D.dtype == F32 else "bf16",
                                      int(bool(accumulate)), int(bias is not None), act, int(res is not None),
-                                     int(aux is not None))))
+                                     int(aux is not None), "gemm")))
     else:
         check(_L().dfu_gemm(ctypes.byref(a), _st()), "dfu_gemm")
     _count()
@@ -248,7 +248,7 @@ def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=N
         e0.record()
         check(_L().dfu_conv_gemm(ctypes.byref(a), st), "dfu_conv_gemm")
         e1.record()
-        GEMM_EVENTS.append((e0, e1, ("conv%d" % mode, B * H * W, Cout, R * S * C, 1, 0, 0, "bf16", 0, 0, 0, 0, 0)))
+        GEMM_EVENTS.append((e0, e1, (B * H * W, Cout, R * S * C, 1, 0, 0, "bf16", 0, 0, 0, 0, 0, "conv%d" % mode)))
     else:
         check(_L().dfu_conv_gemm(ctypes.byref(a), st), "dfu_conv_gemm")
     _count()
@@ -650,7 +650,13 @@ def attention_forward(qkv, B, T, H, scale):
         assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.shape == (B * T, 3 * H * 64)
         out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
         lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+        if GEMM_EVENTS is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(_L().dfu_attention_fwd(_p(qkv), _p(out), _p(lse), B, T, H, scale, _st()), "attention_fwd")
+        if GEMM_EVENTS is not None:
+            e1.record()
+            GEMM_EVENTS.append((e0, e1, (T, T, 128, B * H, 0, 0, "bf16", 0, 0, 0, 0, 0, "attn_fwd")))
         _count()
         return out, lse
     hd = 64
@@ -674,8 +680,14 @@ def attention_backward(qkv, saved, dout, B, T, H, scale, out=None):
         assert out is not None, "the fused backward needs the forward output"
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
+        if GEMM_EVENTS is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(_L().dfu_attention_bwd(_p(qkv), _p(out), _p(dout), _p(saved), _p(dqkv), B, T, H, scale, _st()),
               "attention_bwd")
+        if GEMM_EVENTS is not None:
+            e1.record()
+            GEMM_EVENTS.append((e0, e1, (T, T, 320, B * H, 0, 0, "bf16", 0, 0, 0, 0, 0, "attn_bwd")))
         _count()
         return dqkv
     P = saved
