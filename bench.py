@@ -260,10 +260,12 @@ def main():
         roofline = {"bound": "tensor", "kernel": "dfu_tc_gemm_kernel (+ attn_fwd/attn_bwd): every tcgen05 launch of the step",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the largest GEMM (ViT fc1 forward,
-                    # 25216x3072x768 + GELU + pre-activation copy) from the committed ncu --set full capture
-                    "traffic": {"bytes_per_launch": 294.1e6, "algorithmic_bytes_per_launch": 353.3e6,
-                                "kernel": "dfu_tc_gemm_kernel, ViT fc1 forward", "source": "profiles/r01d_ncu_full_gemm_fc1_fwd.txt"},
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the ViT fc1 weight-gradient GEMM
+                    # (3072x768x25216, CTA-pair kernel, fp32 split-K reduce-add) from the committed ncu --set full capture;
+                    # algorithmic = dY 154.9 MB + X 38.7 MB + dW 9.4 MB
+                    "traffic": {"bytes_per_launch": 207.9e6, "algorithmic_bytes_per_launch": 203.0e6,
+                                "kernel": "dfu_tc_gemm_kernel<.,5,2>, ViT fc1 wgrad",
+                                "source": "profiles/r01k_ncu_full_gemm_pair_fc1_wgrad.txt"},
                     "launches_per_step": n_tc, "attention_launches": n_attn, "tensor_ms_per_step": tc_ms,
                     "tensor_share_of_step": tc_ms / ms_per_step if ms_per_step else None,
                     "note": "achieved = %.3f GFLOP/pair x %d pairs / summed CUDA-event time (launching stream, GPU kept "

@@ -257,6 +257,11 @@ constexpr int LN_MAXV = 4;
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y,
                                                         float* __restrict__ stats, long long rows, int D, float eps) {
+    extern __shared__ float sgb[];          // gamma[D], beta[D]: read once per block instead of once per row from L2
+    float* sg = sgb;
+    float* sb = sgb + D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { sg[i] = gamma[i]; sb[i] = beta[i]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int nvec = D >> 3;
@@ -290,10 +295,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
             const int vi = lane + k * 32;
             if (vi < nvec) {
                 float o[8];
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+                const float4 g0 = *reinterpret_cast<const float4*>(sg + vi * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(sg + vi * 8 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sb + vi * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(sb + vi * 8 + 4);
                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -314,7 +319,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
                                                                const bf16* __restrict__ dres, bf16* __restrict__ dx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                long long rows, int D) {
-    extern __shared__ float sh[];   // [2][8][D/8]: element (col = vi*8+i) of plane p lives at p*D + i*(D/8) + vi
+    extern __shared__ float sh[];   // [2][8][D/8]: element (col = vi*8+i) of plane p lives at p*D + i*(D/8) + vi; then gamma[D]
+    float* sgam = sh + 2 * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sgam[i] = gamma[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -345,8 +353,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
                 float xv[8], dv[8];
                 unpack8(xr[k], xv);
                 unpack8(dr[k], dv);
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -368,8 +376,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
                 float xv[8], dv[8], o[8];
                 unpack8(xr[k], xv);
                 unpack8(dr[k], dv);
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[i] * gg[i] - c1 - (xv[i] - mean) * rstd * c2);
@@ -527,7 +535,7 @@ extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, co
 extern "C" int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
                              int32_t D, float eps, void* stream) {
     DFU_CHECK_ARG(x && gamma && beta && y && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256, "dfu_layernorm: unsupported D=%d", D);
-    layernorm_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
+    layernorm_kernel<<<grid_cap((rows + 7) / 8, 3), 256, 2 * (size_t)D * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
                                                                                    stats, rows, D, eps);
     DFU_CHECK_LAUNCH("layernorm");
     return DFU_OK;
@@ -537,7 +545,7 @@ extern "C" int dfu_layernorm_bwd(const void* dy, const void* x, const float* gam
     DFU_CHECK_ARG(dy && x && gamma && stats && dx && dgamma && dbeta && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256,
                   "dfu_layernorm_bwd: unsupported D=%d", D);
     const int grid = grid_cap((rows + 7) / 8, 2);
-    const size_t smem = 2 * (size_t)D * sizeof(float);
+    const size_t smem = 3 * (size_t)D * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     const int nv = (D / 8 + 31) / 32;
 #define DFU_LN_BWD(NV)                                                                                              \

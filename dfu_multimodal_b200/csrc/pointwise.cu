@@ -80,6 +80,68 @@ __global__ void __launch_bounds__(256) zero_kernel(unsigned char* __restrict__ p
     }
 }
 
+// dx = dy * gelu'(h) and, in the same pass, colsum[n] += sum_m dx[m, n] (the bias gradient of the Linear that produced h).
+// Block = 128 column vectors (1024 columns) x 2 row lanes; GB_UNROLL rows per thread in flight.
+constexpr int GB_UNROLL = 4;
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
+                                                              bf16* __restrict__ dx, float* __restrict__ colsum, long long M,
+                                                              int N) {
+    __shared__ float red[128][9];
+    const int cvl = threadIdx.x & 127, rl = threadIdx.x >> 7;
+    const int cv = blockIdx.y * 128 + cvl;                 // column vector (8 columns)
+    const bool col_ok = cv * 8 < N;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const long long rstride = (long long)gridDim.x * 2;
+    if (col_ok) {
+        for (long long r0 = (long long)blockIdx.x * 2 + rl; r0 < M; r0 += rstride * GB_UNROLL) {
+            bf16x8 va[GB_UNROLL], vb[GB_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GB_UNROLL; ++u) {
+                const long long r = r0 + u * rstride;
+                if (r < M) {
+                    va[u] = ld8(dy + r * N + cv * 8);
+                    vb[u] = ld8(h + r * N + cv * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GB_UNROLL; ++u) {
+                const long long r = r0 + u * rstride;
+                if (r >= M) break;
+                float x[8], y[8], o[8];
+                unpack8(va[u], x);
+                unpack8(vb[u], y);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = x[j] * gelu_grad_fast(y[j]);
+                const bf16x8 pk = pack8(o);
+                st8(dx + r * N + cv * 8, pk);
+                float rb[8];
+                unpack8(pk, rb);                               // sum what was stored (the bf16-rounded values)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += rb[j];
+            }
+        }
+    }
+    if (rl == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[cvl][i] = acc[i];
+    }
+    __syncthreads();
+    if (rl == 0 && col_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += red[cvl][i];
+        // one lane per 8 columns: transposed through shared memory so that consecutive lanes hit consecutive addresses
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[cvl][i] = acc[i];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 1024; t += 256) {
+        const int col = blockIdx.y * 1024 + t;
+        if (col < N) atomicAdd(colsum + col, red[t >> 3][t & 7]);
+    }
+}
+
 // Column sums of x[M, N] (row stride ld) added into out[N].  Block = 32 column-vectors x 8 row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M, int N,
                                                      long long ld, int rows_per_block) {
@@ -384,6 +446,19 @@ extern "C" int dfu_gelu_bwd(const void* dy, const void* h, void* dx, int64_t n, 
     return launch_binary<3>(dy, h, dx, n, stream, "dfu_gelu_bwd");
 }
 
+extern "C" int dfu_gelu_bwd_colsum(const void* dy, const void* h, void* dx, float* colsum, int64_t M, int32_t N, void* stream) {
+    DFU_CHECK_ARG(dy && h && dx && colsum && M > 0 && N > 0 && N % 8 == 0, "dfu_gelu_bwd_colsum: bad args (N=%d must be a multiple of 8)", N);
+    DFU_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)dx & 15) == 0, "dfu_gelu_bwd_colsum: unaligned");
+    const int ycnt = dfu_cdiv(N, 1024);
+    long long xb = ((long long)dfu_num_sms() * 6 + ycnt - 1) / ycnt;
+    const long long max_xb = (M + 1) / 2;
+    if (xb > max_xb) xb = max_xb;
+    if (xb < 1) xb = 1;
+    gelu_bwd_colsum_kernel<<<dim3((unsigned)xb, (unsigned)ycnt), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dy, (const bf16*)h, (bf16*)dx, colsum, M, N);
+    DFU_CHECK_LAUNCH("dfu_gelu_bwd_colsum");
+    return DFU_OK;
+}
 extern "C" int dfu_colsum(const void* x, float* out, int64_t M, int32_t N, int64_t ld, void* stream) {
     DFU_CHECK_ARG(x && out && M > 0 && N > 0 && ld >= N, "dfu_colsum: bad args");
     cudaStream_t st = (cudaStream_t)stream;

@@ -123,6 +123,7 @@ class Conv2dFn(Function):
         in the dgrad GEMM epilogue instead of by a separate pass.  want_stats=True additionally returns the
         per-channel sum / sum of squares of the output ([2*Cout] fp32), accumulated by the GEMM epilogue from the fp32
         accumulators: the BatchNorm that follows needs no statistics pass of its own."""
+        ctx.set_materialize_grads(False)       # no zero-filled "gradient" for the statistics output
         xn = ops.as_nhwc(x)
         B, H, W, C = xn.shape
         Cout, Cin, R, S = weight.shape
@@ -414,13 +415,13 @@ class MlpFn(Function):
         if FUSE_GELU_BWD:
             db1 = ops.zeros(Hd, F32, g2.device) if (ctx.needs_input_grad[2] and ops.colstats_ok(Hd)) else None
             dh = ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd, res=h, act=3, colstats=db1)
+            if db1 is None and ctx.needs_input_grad[2]:
+                db1 = ops.colsum(dh)
         else:
             # measured on B200 (profiles/r01e): the 3072-wide, K=768 dgrad GEMM is epilogue-bound, so GELU' inside
-            # its epilogue (276 us) loses to the plain GEMM (118 us) + one elementwise pass (124 us)
-            db1 = None
-            dh = ops.gelu_bwd(ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd), h)
-        if db1 is None and ctx.needs_input_grad[2]:
-            db1 = ops.colsum(dh)
+            # its epilogue (276 us) loses to the plain GEMM (118 us) + one elementwise pass, which also produces
+            # fc1's bias gradient (column sums of its output) on the way
+            dh, db1 = ops.gelu_bwd_colsum(ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd), h)
         dw1 = ops.linear_wgrad(dh, x2, D).reshape(w1.shape) if ctx.needs_input_grad[1] else None
         dx = ops.linear_dgrad(dh, shadow(w1, Hd, D), D).view(gy.shape) if ctx.needs_input_grad[0] else None
         return dx, dw1, db1, dw2, db2, (gy if ctx.has_res else None)

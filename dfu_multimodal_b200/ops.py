@@ -522,6 +522,17 @@ def gelu_bwd(dy, h):
     return _binary(_L().dfu_gelu_bwd, "gelu_bwd", dy, h)
 
 
+def gelu_bwd_colsum(dy2d, h2d):
+    """(dy * gelu'(h), column sums of that product) in one pass over dense [M, N] bf16 matrices."""
+    _dense_same_layout(dy2d, h2d)
+    M, N = dy2d.shape
+    dx = torch.empty_like(dy2d)
+    cs = zeros(N, F32, dy2d.device)
+    check(_L().dfu_gelu_bwd_colsum(_p(dy2d), _p(h2d), _p(dx), _p(cs), M, N, _st()), "gelu_bwd_colsum")
+    _count()
+    return dx, cs
+
+
 def colsum(x2d):
     M, N = x2d.shape
     out = zeros(N, F32, x2d.device)

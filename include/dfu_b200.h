@@ -149,6 +149,9 @@ int dfu_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* strea
 int dfu_add(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* dx = dy * gelu'(h) */
 int dfu_gelu_bwd(const void* dy, const void* h, void* dx, int64_t n, void* stream);
+/* dx = dy * gelu'(h) over a dense [M,N] matrix (N % 8 == 0) and colsum[N] (fp32, caller zeroes) += column sums of dx:
+ * the GELU backward and fc1's bias gradient (timm Mlp) in one pass. */
+int dfu_gelu_bwd_colsum(const void* dy, const void* h, void* dx, float* colsum, int64_t M, int32_t N, void* stream);
 /* column sums of a bf16 [M,N] matrix (row stride ld) added into out[N] fp32 (caller zeroes): bias gradients. */
 int dfu_colsum(const void* x, float* out, int64_t M, int32_t N, int64_t ld, void* stream);
 /* strided 2-D copy bf16 (rows x cols), used for concat / cls-token selection. */

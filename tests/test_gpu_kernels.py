@@ -329,6 +329,16 @@ def test_layernorm(ops, dev, rows, D):
     close(db2, bf.grad, 1e-3, 1e-3)
 
 
+@pytest.mark.parametrize("M,N", [(1000, 3072), (7, 1024), (333, 1032), (2, 8)])
+def test_gelu_bwd_with_column_sums(ops, dev, M, N):
+    dy, h = rnd(dev, M, N), rnd(dev, M, N, scale=2.0)
+    dx, cs = ops.gelu_bwd_colsum(dy, h)
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).backward(dy.float())
+    close(dx, hf.grad, 2 * BF16_EPS, 1e-3)
+    close(cs, dx.float().sum(0), 1e-4, 1e-3)               # sums of the stored (bf16) values
+
+
 def test_zero_fill_and_arena(ops, dev):
     for n in (1, 15, 16, 17, 4099):
         raw = torch.full((n + 32,), 7, dtype=torch.uint8, device=dev)
