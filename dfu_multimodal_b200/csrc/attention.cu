@@ -500,8 +500,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                      bf16* __restrict__ dqkv, int B, int T, int H, float scale) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
+    __shared__ uint64_t d_full[2], d_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float lse2_s[KV_ROWS], dsum_s[KV_ROWS];
+    __shared__ float lse2_s[2][KV_ROWS], dsum_s[2][KV_ROWS];     // per-query constants, double-buffered across heads
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NK = (T + 15) & ~15;
@@ -513,6 +514,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&sd_full[b], 1); mbar_init(&tile_full[b], 16); mbar_init(&tile_free[b], 1); }
         mbar_init(&acc_full, 1); mbar_init(&acc_empty, 16); mbar_init(&dq_full, 1); mbar_init(&dq_empty, 16);
+        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], 16); }
         fence_mbar_init();
     }
     if (warp_idx == 2) tmem_alloc(&tmem_slot, 512);
@@ -553,14 +555,15 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             auto issue_sd = [&](int kt, int qc) {
                 const uint32_t tb = tmem + P_SD + (qc & 1) * 128;
                 const uint32_t id = qc == 3 ? idesc_s16 : idesc_s64;
+                // the two accumulation chains are interleaved: successive MMAs into one accumulator serialise on the
+                // tensor pipe's latency, which is what bounds these small (N <= 64) instructions
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
+                for (int k = 0; k < HD / 16; ++k) {
                     tc_mma_f16(tb, make_desc(sK + kt * TILE128_BYTES + k * 32, 16, 1024),
                                make_desc(sQ + qc * 8192 + k * 32, 16, 1024), id, k > 0);
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
                     tc_mma_f16(tb + 64, make_desc(sV + kt * TILE128_BYTES + k * 32, 16, 1024),
                                make_desc(sDO + qc * 8192 + k * 32, 16, 1024), id, k > 0);
+                }
                 tc_commit(&sd_full[qc & 1]);
             };
             int it = 0;
@@ -586,19 +589,24 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                             tc_fence_after();
                         }
                         const int q_steps = qc == 3 ? 1 : 4;
-                        for (int k = 0; k < q_steps; ++k) {
-                            const uint64_t bdo = make_desc(sDO + qc * 8192 + k * 2048, 8192, 1024);
-                            const uint64_t bq = make_desc(sQ + qc * 8192 + k * 2048, 8192, 1024);
-                            tc_mma_f16(tmem + C_DV, make_desc(sPT + b * TILE128_BYTES + k * 32, 16, 1024), bdo, idesc_acc,
-                                       (qc > 0 || k > 0));
-                            tc_mma_f16(tmem + C_DK, make_desc(sDST + b * TILE128_BYTES + k * 32, 16, 1024), bq, idesc_acc,
-                                       (qc > 0 || k > 0));
-                        }
-                        if (b == 1) {
-                            // dQ of the query tile this pair of chunks covers: the two dS^T buffers as one MN-major operand
-                            for (int k = 0; k < key_steps; ++k)
+                        // dV, dK (K = this chunk's queries) and, on the second chunk of a pair, dQ of the query tile the
+                        // pair covers (the two dS^T buffers as one MN-major operand, K = this tile's keys): three
+                        // independent accumulation chains, issued round-robin
+                        const int dq_steps = b == 1 ? key_steps : 0;
+                        for (int k = 0; k < (q_steps > dq_steps ? q_steps : dq_steps); ++k) {
+                            if (k < q_steps) {
+                                const uint64_t bdo = make_desc(sDO + qc * 8192 + k * 2048, 8192, 1024);
+                                const uint64_t bq = make_desc(sQ + qc * 8192 + k * 2048, 8192, 1024);
+                                tc_mma_f16(tmem + C_DV, make_desc(sPT + b * TILE128_BYTES + k * 32, 16, 1024), bdo, idesc_acc,
+                                           (qc > 0 || k > 0));
+                                tc_mma_f16(tmem + C_DK, make_desc(sDST + b * TILE128_BYTES + k * 32, 16, 1024), bq, idesc_acc,
+                                           (qc > 0 || k > 0));
+                            }
+                            if (k < dq_steps)
                                 tc_mma_f16(tmem + C_DQ + (qc >> 1) * HD, make_desc(sDST + k * 2048, TILE128_BYTES, 1024),
                                            make_desc(sK + kt * TILE128_BYTES + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0));
+                        }
+                        if (b == 1) {
                             tc_commit(&tile_free[0]);
                             tc_commit(&tile_free[1]);
                         }
@@ -609,27 +617,17 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 tc_commit(&ops_empty);
             }
         }
-    } else if (warp_idx >= 4) {
-        // 16 warps: warp (quarter, cg) owns TMEM lanes 32*quarter..+31 and 16 of the 64 query columns of each chunk
-        const int ew = warp_idx - 4;
-        const int cg = ew >> 2;
-        const int quarter = warp_idx & 3;
-        const int row = quarter * 32 + lane;
-        const int ct = threadIdx.x - 128;
-        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
-        const float sl2 = scale * LOG2E;
-        const uint32_t sPT = smem_u32(smem + P_PT0) + row * 128;
-        const uint32_t sDST = smem_u32(smem + P_DST0) + row * 128;
+    } else if (warp_idx == 3) {
+        // D[q] = sum_d dO[q,d] O[q,d] and lse[q] * log2(e) of the NEXT head while the other warps work on the current one
         int it = 0;
-        uint32_t use[2] = {0, 0};
-        uint32_t ktg = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int b = w / H, h = w - b * H;
-            named_bar_sync(1, 512);
-            if (ct < KV_ROWS) {
+            const int buf = it & 1;
+            mbar_wait(&d_empty[buf], ((it >> 1) & 1) ^ 1);
+            for (int q = lane; q < KV_ROWS; q += 32) {
                 float d = 0.f, l2 = 0.f;
-                if (ct < T) {
-                    const long long off = ((long long)b * T + ct) * (H * HD) + h * HD;
+                if (q < T) {
+                    const long long off = ((long long)b * T + q) * (H * HD) + h * HD;
                     bf16x8 vo[8], vg[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { vo[k] = ld_global_v4(out + off + k * 8); vg[k] = ld_global_v4(dout + off + k * 8); }
@@ -641,12 +639,33 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 #pragma unroll
                         for (int j = 0; j < 8; ++j) d += fo[j] * fg[j];
                     }
-                    l2 = lse[((long long)b * H + h) * T + ct] * LOG2E;
+                    l2 = lse[((long long)b * H + h) * T + q] * LOG2E;
                 }
-                dsum_s[ct] = d;
-                lse2_s[ct] = l2;
+                dsum_s[buf][q] = d;
+                lse2_s[buf][q] = l2;
             }
-            named_bar_sync(1, 512);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_full[buf]);
+        }
+    } else if (warp_idx >= 4) {
+        // 16 warps: warp (quarter, cg) owns TMEM lanes 32*quarter..+31 and 16 of the 64 query columns of each chunk
+        const int ew = warp_idx - 4;
+        const int cg = ew >> 2;
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = scale * LOG2E;
+        const uint32_t sPT = smem_u32(smem + P_PT0) + row * 128;
+        const uint32_t sDST = smem_u32(smem + P_DST0) + row * 128;
+        int it = 0;
+        uint32_t use[2] = {0, 0};
+        uint32_t ktg = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            const int b = w / H, h = w - b * H;
+            const int dbuf = it & 1;
+            mbar_wait(&d_full[dbuf], (it >> 1) & 1);         // this head's per-query constants (written by warp 3)
+            const float* lse2c = lse2_s[dbuf];
+            const float* dsumc = dsum_s[dbuf];
             for (int kt = 0; kt < 2; ++kt, ++ktg) {
                 const int key = kt * 128 + row;
                 const bool key_ok = key < T;
@@ -664,10 +683,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int q = qc * 64 + cg * 16 + j;
-                            const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lse2_s[q]);
+                            const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lse2c[q]);
                             const bool ok = key_ok && (q < T);
                             p[j] = ok ? e : 0.f;
-                            ds[j] = ok ? e * (__uint_as_float(dp[j]) - dsum_s[q]) * scale : 0.f;
+                            ds[j] = ok ? e * (__uint_as_float(dp[j]) - dsumc[q]) * scale : 0.f;
                         }
                     }
                     // the MMAs of the pair that last used this smem buffer have finished reading it
@@ -708,6 +727,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[dbuf]);
             mbar_wait(&dq_full, it & 1);
             tc_fence_after();
             {

@@ -124,20 +124,47 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
     mean_invstd[C + c] = rsqrtf(rv[c] + eps);
 }
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
+// `sums` non-null: training-mode call that also does the finalize step -- every thread derives mean / invstd of its 8
+// channels from the batch sums, block 0 stores them (for the backward pass) and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ y, float* __restrict__ mean_invstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const bf16* __restrict__ res, bf16* __restrict__ z, long long M,
-                                                       int C, int relu) {
+                                                       int C, int relu, const float* __restrict__ sums,
+                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                       long long* __restrict__ nbt, float eps, float momentum) {
     const int cvec = C >> 3;
     const int rows_per_iter = 256 / cvec;
     const int cv = threadIdx.x % cvec;
     const int rl = threadIdx.x / cvec;
     float sc[8], sh[8];
+    if (sums) {
+        const float inv_m = 1.f / (float)M;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = cv * 8 + i;
-        sc[i] = gamma[c] * mean_invstd[C + c];
-        sh[i] = beta[c] - mean_invstd[c] * sc[i];
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            const float mean = sums[c] * inv_m;
+            const float var = fmaxf(sums[C + c] * inv_m - mean * mean, 0.f);
+            const float invstd = rsqrtf(var + eps);
+            if (blockIdx.x == 0 && rl == 0) {
+                mean_invstd[c] = mean;
+                mean_invstd[C + c] = invstd;
+                if (running_mean) {
+                    const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+                }
+            }
+            sc[i] = gamma[c] * invstd;
+            sh[i] = beta[c] - mean * sc[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            sc[i] = gamma[c] * mean_invstd[C + c];
+            sh[i] = beta[c] - mean_invstd[c] * sc[i];
+        }
     }
     const long long rstride = (long long)gridDim.x * rows_per_iter;
     for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
@@ -505,8 +532,22 @@ extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float
                   (long long)M, C);
     const int rpi = 256 / (C / 8);
     bn_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu);
+        (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, nullptr, nullptr,
+        nullptr, nullptr, 0.f, 0.f);
     DFU_CHECK_LAUNCH("bn_apply");
+    return DFU_OK;
+}
+extern "C" int dfu_bn_apply_train(const void* y, const float* sums, const float* gamma, const float* beta, const void* res, void* z,
+                                  float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                  int64_t M, int32_t C, int32_t relu, float eps, float momentum, void* stream) {
+    DFU_CHECK_ARG(y && sums && gamma && beta && z && mean_invstd && M > 0 && bn_shape_ok(C),
+                  "dfu_bn_apply_train: unsupported shape M=%lld C=%d", (long long)M, C);
+    DFU_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "dfu_bn_apply_train: running_mean/var go together");
+    const int rpi = 256 / (C / 8);
+    bn_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, sums, running_mean, running_var,
+        (long long*)num_batches_tracked, eps, momentum);
+    DFU_CHECK_LAUNCH("bn_apply_train");
     return DFU_OK;
 }
 extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,

@@ -396,21 +396,22 @@ def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, tr
     dev = y2d.device
     mean_invstd = torch.empty(2 * C, dtype=F32, device=dev)
     L = _L()
+    z = torch.empty_like(y2d)
     if training:
         if sums is None:
             sums = zeros(2 * C, F32, dev)
             check(L.dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
             _count()
-        check(L.dfu_bn_finalize(_p(sums), _p(mean_invstd), _p(running_mean), _p(running_var), _p(nbt), M, C, eps,
-                                momentum, _st()), "bn_finalize")
+        # finalize (mean/invstd, running statistics) and apply in one launch
+        check(L.dfu_bn_apply_train(_p(y2d), _p(sums), _p(gamma), _p(beta), _p(res2d), _p(z), _p(mean_invstd),
+                                   _p(running_mean), _p(running_var), _p(nbt), M, C, 1 if relu else 0, eps, momentum,
+                                   _st()), "bn_apply_train")
         _count()
-    else:
-        check(L.dfu_bn_eval_stats(_p(running_mean), _p(running_var), _p(mean_invstd), C, eps, _st()), "bn_eval_stats")
-        _count()
-    z = torch.empty_like(y2d)
+        return z, mean_invstd
+    check(L.dfu_bn_eval_stats(_p(running_mean), _p(running_var), _p(mean_invstd), C, eps, _st()), "bn_eval_stats")
     check(L.dfu_bn_apply(_p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(res2d), _p(z), M, C, 1 if relu else 0,
                          _st()), "bn_apply")
-    _count()
+    _count(2)
     return z, mean_invstd
 
 

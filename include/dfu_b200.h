@@ -121,6 +121,11 @@ int dfu_bn_eval_stats(const float* running_mean, const float* running_var, float
 /* z = [relu]( gamma*(y-mean)*invstd + beta [+ res] ) */
 int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
                  void* z, int64_t M, int32_t C, int32_t relu, void* stream);
+/* train(): dfu_bn_finalize and dfu_bn_apply in one launch -- mean/invstd from the batch sums (stored to mean_invstd for the
+ * backward pass), running statistics and num_batches_tracked updated, then z = [relu](gamma*xhat + beta [+ res]). */
+int dfu_bn_apply_train(const void* y, const float* sums, const float* gamma, const float* beta, const void* res, void* z,
+                       float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       int64_t M, int32_t C, int32_t relu, float eps, float momentum, void* stream);
 /* Backward pass 1: sums[0:C] += sum(dpre), sums[C:2C] += sum(dpre*xhat), dpre = dz*(z>0 if relu).
  * z may be null when the block had no residual input: the mask is then recomputed from y as gamma*xhat+beta > 0
  * (gamma, beta required), which saves reading z. */
