@@ -34,6 +34,7 @@ class ConvArgs(ctypes.Structure):
         ("Cout", ctypes.c_int32), ("R", ctypes.c_int32), ("S", ctypes.c_int32), ("stride", ctypes.c_int32), ("pad", ctypes.c_int32),
         ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("ldw", ctypes.c_int64), ("dy", ctypes.c_void_p),
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64), ("accumulate", ctypes.c_int32), ("max_ctas", ctypes.c_int32),
+        ("colstats", ctypes.c_void_p),
     ]
 
 

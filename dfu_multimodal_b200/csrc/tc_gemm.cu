@@ -567,49 +567,36 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
                         }
                     }
-                    if (CS && p.colstats) {
-                        // column sums of this warp's 32 rows: butterfly reduce-scatter, lane j ends with column j
-                        if (!row_ok) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        }
-                        float* sq = reinterpret_cast<float*>(r);        // the raw accumulators are dead by now
-                        if (p.colstats_mode == 2) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-                        }
-#pragma unroll
-                        for (int sft = 16; sft >= 1; sft >>= 1) {
-                            const bool up = (lane & sft) != 0;
-#pragma unroll
-                            for (int i2 = 0; i2 < sft; ++i2) {
-                                const float send = up ? v[i2] : v[i2 + sft];
-                                const float keep = up ? v[i2 + sft] : v[i2];
-                                v[i2] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-                            }
-                        }
-                        if (p.colstats_mode == 2) {
-#pragma unroll
-                            for (int sft = 16; sft >= 1; sft >>= 1) {
-                                const bool up = (lane & sft) != 0;
-#pragma unroll
-                                for (int i2 = 0; i2 < sft; ++i2) {
-                                    const float send = up ? sq[i2] : sq[i2 + sft];
-                                    const float keep = up ? sq[i2 + sft] : sq[i2];
-                                    sq[i2] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-                                }
-                            }
-                        }
-                        const int col = nbase + lane;
-                        if (col < p.N) {
-                            atomicAdd(colacc + col, v[0]);
-                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col, sq[0]);
-                        }
-                    }
                 };
                 auto store_slab = [&](int sl) {
                     const int ncol0 = n_tile * p.block_n + sl * slab_cols;
                     uint8_t* const stg_out = stg_base + bufsel * set_bytes;
+                    if (CS && p.colstats && !f_fp32) {
+                        // column statistics of the slab just staged (32 rows x 64 bf16 columns): lane L walks column pair
+                        // (2L, 2L+1) down the swizzled slab (conflict-free), then one shared-memory atomic per column
+                        __syncwarp();
+                        const uint32_t sbase = smem_u32(stg_out) + (lane & 3) * 4;
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            if (row0 + r < p.M) {                        // warp-uniform
+                                uint32_t w;
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+                                const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
+                                s0 += f.x; s1 += f.y;
+                                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                            }
+                        }
+                        const int col = ncol0 + 2 * lane;
+                        if (col < p.N) {
+                            atomicAdd(colacc + col, s0);
+                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col, q0);
+                        }
+                        if (col + 1 < p.N) {
+                            atomicAdd(colacc + col + 1, s1);
+                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col + 1, q1);
+                        }
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -958,7 +945,7 @@ cudaError_t set_smem_attrs() {
 #define DFU_SET_ATTR(CS, EM, CG)                                                                                     \
     if (e == cudaSuccess)                                                                                            \
         e = cudaFuncSetAttribute(dfu_tc_gemm_kernel<CS, EM, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
-    DFU_SET_ATTR(true, 0, 1); DFU_SET_ATTR(false, 0, 1); DFU_SET_ATTR(false, 1, 1); DFU_SET_ATTR(false, 2, 1);
+    DFU_SET_ATTR(true, 0, 1); DFU_SET_ATTR(true, 1, 1); DFU_SET_ATTR(false, 0, 1); DFU_SET_ATTR(false, 1, 1); DFU_SET_ATTR(false, 2, 1);
     DFU_SET_ATTR(false, 3, 1); DFU_SET_ATTR(false, 4, 1); DFU_SET_ATTR(false, 5, 1);
     DFU_SET_ATTR(false, 1, 2); DFU_SET_ATTR(false, 2, 2); DFU_SET_ATTR(false, 3, 2); DFU_SET_ATTR(false, 4, 2);
     DFU_SET_ATTR(false, 5, 2);
@@ -968,7 +955,8 @@ cudaError_t set_smem_attrs() {
 
 // Which epilogue instantiation serves this launch (-1: the one with the column-statistics code).
 int pick_epilogue_mode(const GemmParams& p) {
-    if (p.colstats) return -1;
+    if (p.colstats)      // -1: general epilogue + column statistics; -2: plain bf16 store + column statistics
+        return (p.tma_store && p.alpha == 1.f && !p.d_fp32 && !p.bias && !p.res && !p.aux && p.act == 0) ? -2 : -1;
     if (!p.tma_store || p.alpha != 1.f) return 0;
     const bool bias = p.bias != nullptr, res = p.res != nullptr, aux = p.aux != nullptr;
     if (p.d_fp32) return (!bias && !res && !aux && p.act == 0) ? 5 : 0;
@@ -1011,6 +999,7 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
     }
     switch (em) {
         case -1: dfu_tc_gemm_kernel<true, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case -2: dfu_tc_gemm_kernel<true, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 1: dfu_tc_gemm_kernel<false, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 2: dfu_tc_gemm_kernel<false, 2, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 3: dfu_tc_gemm_kernel<false, 3, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
@@ -1032,8 +1021,9 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias || a->colstats)),
                   "dfu_gemm: accumulate mode takes no bias/act/res/aux/colstats");
     DFU_CHECK_ARG(a->act >= 0 && a->act <= 3 && !(a->act == 3 && !a->res), "dfu_gemm: act=%d (3 needs res = pre-activation)", a->act);
-    DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && a->N <= 2048 && a->nb0 * a->nb1 == 1),
-                  "dfu_gemm: colstats needs mode 1|2, N <= 2048 and no batching");
+    DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && a->N <= 2048 && a->nb0 * a->nb1 == 1 &&
+                                   a->d_dtype == 0),
+                  "dfu_gemm: colstats needs mode 1|2, N <= 2048, a bf16 output and no batching");
 
     const bool batched = (a->nb0 * a->nb1) > 1;
     bool tma_ok = aligned16(a->A) && aligned16(a->B) && (a->lda % 8 == 0) && (a->ldb % 8 == 0);
@@ -1203,6 +1193,12 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     p.epi_bufs = 1;
     p.vec_ok = 1;
     p.cv_mode = a->mode;
+    if (a->colstats) {
+        DFU_CHECK_ARG(a->mode == 1 && a->Cout <= 2048, "dfu_conv_gemm: colstats is a forward-mode feature (Cout <= 2048)");
+        p.colstats = a->colstats;
+        p.colstats_mode = 2;
+        p.stages = 3;                    // the per-column accumulators take the fourth stage's shared memory
+    }
     p.cv_S = a->S;
     p.cv_pad = a->pad;
     p.cv_C = a->C;

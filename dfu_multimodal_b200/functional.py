@@ -14,7 +14,7 @@ from .ops import BF16, F32
 # Epilogue fusions that are implemented and parity-tested but lose on B200 at the benchmark shapes because the GEMMs
 # they attach to are epilogue-bound (small K): measured numbers in profiles/r01e_gemm_bench_isolated.txt.
 FUSE_GELU_BWD = os.environ.get("DFU_FUSE_GELU_BWD", "0") == "1"     # GELU' in the fc2-dgrad epilogue (act=3)
-FUSE_BN_STATS = os.environ.get("DFU_FUSE_BN_STATS", "0") == "1"     # BatchNorm sums in the conv GEMM epilogue (colstats)
+FUSE_BN_STATS = os.environ.get("DFU_FUSE_BN_STATS", "1") == "1"     # BatchNorm sums in the conv GEMM epilogue (colstats)
 FUSE_SKIP_DGRAD = os.environ.get("DFU_FUSE_SKIP_DGRAD", "0") == "1"  # skip-connection gradient in the conv1 dgrad epilogue
 
 
@@ -136,8 +136,10 @@ class Conv2dFn(Function):
         implicit = ops.conv_implicit_ok(C, Cout, R, S, stride)
         if implicit:
             # tiles gathered by TMA straight from the activation tensor: no im2col matrix, x itself is what is saved
-            y = ops.conv_forward(xn, wm, R, S, pad).view(B * Ho * Wo, Cout)
-            sums = ops.bn_stats(y) if want_stats else None
+            sums = ops.zeros(2 * Cout, F32, xn.device) if (want_stats and FUSE_BN_STATS and Cout <= 2048) else None
+            y = ops.conv_forward(xn, wm, R, S, pad, colstats=sums).view(B * Ho * Wo, Cout)
+            if want_stats and sums is None:
+                sums = ops.bn_stats(y)
             ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, False)
             ctx.implicit = True
             ctx.save_for_backward(xn, weight)

@@ -236,12 +236,13 @@ def conv_implicit_ok(C, Cout, R, S, stride):
     return _CONV_IMPL == "implicit" and stride == 1 and R * S > 1 and C % 64 == 0 and Cout % 64 == 0
 
 
-def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False):
+def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False, colstats=None):
     a = ConvArgs()
     a.mode, a.B, a.H, a.W, a.C = mode, B, H, W, C
     a.Cout, a.R, a.S, a.stride, a.pad = Cout, R, S, 1, pad
     a.x, a.w, a.ldw, a.dy = _p(x), _p(w), (w.stride(0) if w is not None else 0), _p(dy)
     a.out, a.ldo, a.accumulate, a.max_ctas = _p(out), ldo, 1 if accumulate else 0, 0
+    a.colstats = _p(colstats)
     st = _st()
     if GEMM_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,14 +256,15 @@ def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=N
     return out
 
 
-def conv_forward(x_nhwc, wm, R, S, pad):
-    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1."""
+def conv_forward(x_nhwc, wm, R, S, pad, colstats=None):
+    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1.
+    colstats ([2*Cout] fp32, zeroed) += per-channel sum / sum of squares of y (BatchNorm batch statistics)."""
     _need_cuda(x_nhwc, wm)
     B, H, W, C = x_nhwc.shape
     Cout = wm.shape[0]
     Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
     y = torch.empty((B, Ho, Wo, Cout), dtype=BF16, device=x_nhwc.device)
-    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y)
+    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats)
 
 
 def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad):

@@ -43,7 +43,8 @@ int dfu_set_sm_budget(int32_t n_sms);
  *   aux (bf16, same geometry as D) receives the pre-activation value when non-null.
  *   act: 0 none, 1 relu, 2 gelu(erf), 3 = D = (alpha*acc + bias) * gelu'(res) (res holds the pre-activation; fuses the
  *   GELU backward into the dgrad GEMM).  impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
- *   colstats (fp32, caller zeroes; tcgen05 kernel only, N <= 2048, unbatched): += per-column sums of D over the M rows
+ *   colstats (fp32, caller zeroes; tcgen05 kernel only, bf16 output, N <= 2048, unbatched): += per-column sums of the
+ *   stored (bf16-rounded) D over the M rows
  *   (mode 1: sums[N]) and sums of squares (mode 2: sums[N], sumsq[N]) -- BatchNorm batch statistics straight from the
  *   convolution GEMM, bias gradients straight from the dgrad GEMM.
  * ------------------------------------------------------------------------------------------- */
@@ -85,6 +86,7 @@ typedef struct {
     void* out; int64_t ldo;
     int32_t accumulate;
     int32_t max_ctas;
+    float* colstats;   /* mode 1 only, may be null: [2*Cout] fp32 (caller zeroes) += per-channel sum and sum of squares of y */
 } dfu_conv_args;
 int dfu_conv_gemm(const dfu_conv_args* a, void* stream);
 

@@ -106,7 +106,7 @@ def test_gemm_gelu_grad_epilogue(ops, dev, M, N, K, impl):
 @pytest.mark.parametrize("M,N,K,mode,bias", [(5000, 256, 64, 2, 0), (777, 2048, 512, 2, 0), (1000, 3072, 768, 1, 0),
                                              (300, 64, 147 + 5, 2, 0), (130, 200, 96, 1, 1)])
 def test_gemm_column_statistics_epilogue(ops, dev, M, N, K, mode, bias):
-    """colstats: per-column sum (and sum of squares) of the fp32 results, accumulated by the epilogue."""
+    """colstats: per-column sum (and sum of squares) of the stored results, accumulated by the epilogue."""
     if not ops.colstats_ok(N):
         pytest.skip("N outside the epilogue reduction's range")
     A, B = rnd(dev, M, K), rnd(dev, N, K)
@@ -118,9 +118,11 @@ def test_gemm_column_statistics_epilogue(ops, dev, M, N, K, mode, bias):
     if bias:
         ref = ref + bias_t
     close(D, ref, 2 * BF16_EPS, 1e-3)
-    close(st[:N], ref.sum(0), 1e-3, 1e-2 * (M ** 0.5))
+    # the statistics are those of the STORED (bf16-rounded) output, exactly what a separate pass over D would compute
+    Df = D.float()
+    close(st[:N], Df.sum(0), 1e-4, 1e-3)
     if mode == 2:
-        close(st[N:], (ref * ref).sum(0), 1e-3, 1e-2 * (M ** 0.5))
+        close(st[N:], (Df * Df).sum(0), 1e-4, 1e-3)
 
 
 def test_gemm_alpha_and_padded_leading_dims(ops, dev):
