@@ -69,6 +69,7 @@ struct GemmParams {
     int cv_cchunks;           // 64-channel chunks of the gathered tensor (fwd: Cin/64, dgrad: Cout/64)
     int cv_C;                 // channels of the tap-major weight columns (Cin)
     int cv_sh, cv_sb;         // epilogue slab = 32 tile rows = box (cv_wb, cv_sh, cv_sb)
+    int cv_ow, cv_oh, cv_nb;  // extent of the output image batch (tile rows beyond it are clipped by the TMA store)
     float* colstats;   // per-column sum (and sum of squares) of D accumulated here when non-null
     int colstats_mode; // 1: sums[N]; 2: sums[N] then sums of squares[N]
     int res_vec;
@@ -579,7 +580,16 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
-                            if (row0 + r < p.M) {                        // warp-uniform
+                            bool row_in = row0 + r < p.M;                // warp-uniform
+                            if (p.cv_mode) {
+                                // a tile row outside the image still holds a value (its taps reach inside): not a sample
+                                const int idx = quarter * 32 + r;
+                                const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
+                                row_in = wt * p.cv_wb + idx % p.cv_wb < p.cv_ow &&
+                                         ht * p.cv_hb + (idx / p.cv_wb) % p.cv_hb < p.cv_oh &&
+                                         bt * p.cv_bb + idx / (p.cv_wb * p.cv_hb) < p.cv_nb;
+                            }
+                            if (row_in) {
                                 uint32_t w;
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
                                 const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
@@ -1219,6 +1229,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         pick_pixel_box(OW, OH, a->B, BLOCK_M, &p.cv_wb, &p.cv_hb, &p.cv_bb);
         p.cv_tw = dfu_cdiv(OW, p.cv_wb);
         p.cv_th = dfu_cdiv(OH, p.cv_hb);
+        p.cv_ow = OW; p.cv_oh = OH; p.cv_nb = a->B;
         p.m_tiles = p.cv_tw * p.cv_th * dfu_cdiv(a->B, p.cv_bb);
         p.M = p.m_tiles * BLOCK_M;
         p.N = fwd ? a->Cout : a->C;

@@ -233,9 +233,14 @@ def test_implicit_gemm_convolution(ops, dev, B, H, W, C, Cout, R, pad):
     xf, wf = x.double().cpu().requires_grad_(True), w.double().cpu().requires_grad_(True)
     ref = F.conv2d(xf, wf, padding=pad)
     Ho, Wo = ref.shape[2], ref.shape[3]
-    y = ops.conv_forward(xn, wm, R, R, pad)
+    st = torch.zeros(2 * Cout, dtype=torch.float32, device=dev)
+    y = ops.conv_forward(xn, wm, R, R, pad, colstats=st)
     assert y.shape == (B, Ho, Wo, Cout)
     close(y.permute(0, 3, 1, 2), ref, 2 * BF16_EPS, 2e-3)
+    # BatchNorm batch sums from the epilogue == a pass over the stored output (tile rows outside the image excluded)
+    yf = y.float().reshape(-1, Cout)
+    close(st[:Cout], yf.sum(0), 1e-4, 1e-3)
+    close(st[Cout:], (yf * yf).sum(0), 1e-4, 1e-3)
     dy = rnd(dev, B, Cout, Ho, Wo)
     ref.backward(dy.double().cpu())
     dyn = dy.permute(0, 2, 3, 1).contiguous()

@@ -329,3 +329,17 @@ def test_checkpoint_written_by_train_scheme_loads_and_predicts(R, D, dev, tmp_pa
         a = model(rgb_u8.to(dev), th_u8.to(dev)).cpu()
         b = oracle(R.preprocess(rgb_u8, "imagenet"), R.preprocess(th_u8, "half"))
     assert (a - b).abs().max().item() < LOGIT_TOL
+
+
+def test_device_prefetcher_yields_batches_in_order(dev):
+    from dfu_multimodal_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(1)
+    host = [(torch.randint(0, 256, (4, 8, 8, 3), generator=g, dtype=torch.uint8).pin_memory(),
+             torch.full((4,), i, dtype=torch.int64).pin_memory()) for i in range(7)]
+    seen = []
+    for img, lab in DevicePrefetcher(iter(host), dev):
+        assert img.is_cuda and lab.is_cuda
+        seen.append((img.cpu().clone(), lab.cpu().clone()))
+    assert len(seen) == 7
+    for (hi, hl), (si, sl) in zip(host, seen):
+        assert torch.equal(hi, si) and torch.equal(hl, sl)
