@@ -306,7 +306,13 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured CUDA graphs hold NCCL work on the communicator: tearing the process group down while they are alive
+        # blocks (measured: destroy_process_group never returns).  All ranks are done and in step here, so leave directly.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -210,18 +210,23 @@ __global__ void __launch_bounds__(256) im2col_scalar_kernel(const bf16* __restri
 // output row touches are staged in shared memory with 128-bit loads, then every thread assembles 8 consecutive
 // columns of one col row (k = (r*S + s)*3 + c, i.e. S*3 contiguous input elements per filter row) and writes them
 // with one 128-bit store; consecutive threads write consecutive 16-byte chunks, so stores are fully coalesced.
+constexpr int C3_ROWS_PER_BLOCK = 4;      // output rows per block (their input rows overlap: staged once)
 __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W,
                                                         int R, int S, int stride, int pad, int Ho, int Wo,
                                                         int ldc) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [R][W*3]
-    const int ho = blockIdx.x % Ho;
-    const int b = blockIdx.x / Ho;
+    bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [(C3_ROWS_PER_BLOCK-1)*stride + R][W*3]
+    const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
+    const int ho0 = (blockIdx.x % hblocks) * C3_ROWS_PER_BLOCK;
+    const int b = blockIdx.x / hblocks;
+    const int nho = min(C3_ROWS_PER_BLOCK, Ho - ho0);
+    const int nrows = (nho - 1) * stride + R;
     const int rowlen = W * 3;
     const int vec_per_row = rowlen >> 3;
-    for (int t = threadIdx.x; t < R * vec_per_row; t += blockDim.x) {
+    const int h_first = ho0 * stride - pad;
+    for (int t = threadIdx.x; t < nrows * vec_per_row; t += blockDim.x) {
         const int r = t / vec_per_row, v = t - r * vec_per_row;
-        const int h = ho * stride - pad + r;
+        const int h = h_first + r;
         bf16x8 val;
         if (h >= 0 && h < H) {
             val = ld8(x + ((long long)b * H + h) * rowlen + v * 8);
@@ -235,11 +240,15 @@ __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__
     const int chunks = ldc >> 3;
     const int Kc = R * S * 3;
     const int seg = S * 3;
-    bf16* out = col + ((long long)b * Ho + ho) * Wo * ldc;
     const bf16 zero = __float2bfloat16(0.f);
-    for (int t = threadIdx.x; t < Wo * chunks; t += blockDim.x) {
-        const int wo = t / chunks, ch = t - wo * chunks;
+    bf16* out = col + ((long long)b * Ho + ho0) * Wo * ldc;
+    const int per_row = Wo * chunks;
+    for (int t = threadIdx.x; t < nho * per_row; t += blockDim.x) {
+        const int hl = t / per_row;
+        const int tt = t - hl * per_row;
+        const int wo = tt / chunks, ch = tt - wo * chunks;
         const int w0 = (wo * stride - pad) * 3;
+        const bf16* base = rows + hl * stride * rowlen;
         alignas(16) bf16 e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__
             if (k < Kc) {
                 const int r = k / seg, j = k - r * seg;
                 const int we = w0 + j;
-                if (we >= 0 && we < rowlen) v = rows[r * rowlen + we];
+                if (we >= 0 && we < rowlen) v = base[r * rowlen + we];
             }
             e[i] = v;
         }
@@ -409,9 +418,10 @@ extern "C" int dfu_im2col_nhwc(const void* x, void* col, int32_t B, int32_t H, i
             DFU_CHECK_LAUNCH("zero_pad_cols");
         }
     } else if (C == 3 && (W * 3) % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0 &&
-               (size_t)R * W * 3 * sizeof(bf16) <= 48 * 1024) {
-        im2col_c3_kernel<<<B * Ho, 256, (size_t)R * W * 3 * sizeof(bf16), st>>>((const bf16*)x, (bf16*)col, H, W, R, S, stride,
-                                                                            pad, Ho, Wo, (int)ldc);
+               (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16) <= 48 * 1024) {
+        const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
+        im2col_c3_kernel<<<B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16), st>>>(
+            (const bf16*)x, (bf16*)col, H, W, R, S, stride, pad, Ho, Wo, (int)ldc);
         DFU_CHECK_LAUNCH("im2col_c3");
     } else {
         im2col_scalar_kernel<<<grid_for(rows * ldc, 256, 16), 256, 0, st>>>((const bf16*)x, (bf16*)col, B, H, W, C, R, S,
