@@ -103,8 +103,10 @@ def run_reference(args):
         "impl": "reference", "metric": "fusion_train_pairs_per_sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ResNet50+ViT-B/16 late-fusion train step (config 3), CPU sample of %d pairs/step" % B,
-                   "global_batch": B, "image": "224x224x3 uint8 pairs", "optimizer": "AdamW lr1e-4 wd1e-4"},
+        "config": {"workload": "config 3: ResNet50+ViT-B/16 late-fusion train step, batch 128 pairs, 1 B200",
+                   "global_batch": CONFIG3_BATCH, "per_gpu_batch": CONFIG3_BATCH, "image": "224x224x3 uint8 pairs",
+                   "optimizer": "AdamW lr1e-4 wd1e-4", "loss": "class-weighted CE",
+                   "sample": "each timed step = the same fp32 train step on %d pairs (bounded CPU sample of the workload)" % B},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": "oracle/reference_model.py fusion train step, B=%d, %d timed steps after %d warm-up, "
                                    "os.cpu_count()=%s" % (B, steps, warmup, os.cpu_count())},
