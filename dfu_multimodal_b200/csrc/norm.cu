@@ -20,7 +20,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z,
                                                         const bf16* __restrict__ y, const float* __restrict__ mean_invstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ sums, long long M, int C, int relu) {
+                                                        float* __restrict__ sums, long long M, int C, int relu,
+                                                        const unsigned char* __restrict__ zmask) {
     __shared__ float red[2][256][9];   // padded against bank conflicts
     const int cvec = C >> 3;
     const int rows_per_iter = 256 / cvec;
@@ -31,7 +32,8 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restric
     for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
     // xhat = xa*y + xb;  mask (no saved z): mp*y + mq > 0
     float xa[8], xb[8], mp[8], mq[8];
-    const bool mask_from_y = MODE == 1 && relu && z == nullptr;
+    const bool mask_from_y = MODE == 1 && relu && z == nullptr && zmask == nullptr;
+    const bool use_bits = MODE == 1 && relu && zmask != nullptr;     // 1 bit per element saved by the forward pass
     if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restric
     const long long rstride = (long long)gridDim.x * rows_per_iter;
     for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
         bf16x8 va[BN_UNROLL], vy[BN_UNROLL], vz[BN_UNROLL];
+        unsigned int mb[BN_UNROLL];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
             const long long r = r0 + u * rstride;
@@ -54,7 +57,8 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restric
                 va[u] = ld8(a + off);
                 if (MODE == 1) {
                     vy[u] = ld8(y + off);
-                    if (relu && !mask_from_y) vz[u] = ld8(z + off);
+                    if (use_bits) mb[u] = zmask[r * cvec + cv];
+                    else if (relu && !mask_from_y) vz[u] = ld8(z + off);
                 }
             }
         }
@@ -70,7 +74,10 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const bf16* __restric
             } else {
                 float zz[8], yy[8];
                 unpack8(vy[u], yy);
-                if (relu && !mask_from_y) {
+                if (use_bits) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (!((mb[u] >> i) & 1u)) f[i] = 0.f;
+                } else if (relu && !mask_from_y) {
                     unpack8(vz[u], zz);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) if (!(zz[i] > 0.f)) f[i] = 0.f;
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ res, bf16* __restrict__ z, long long M,
                                                        int C, int relu, const float* __restrict__ sums,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                       long long* __restrict__ nbt, float eps, float momentum) {
+                                                       long long* __restrict__ nbt, float eps, float momentum,
+                                                       unsigned char* __restrict__ zmask) {
     const int cvec = C >> 3;
     const int rows_per_iter = 256 / cvec;
     const int cv = threadIdx.x % cvec;
@@ -193,6 +201,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
                 for (int i = 0; i < 8; ++i) f[i] += rr[i];
             }
             if (relu) {
+                if (zmask) {                 // ReLU mask for the backward pass: 1 bit per element instead of re-reading z
+                    unsigned int bits = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bits |= (f[i] > 0.f ? 1u : 0u) << i;
+                    zmask[r * cvec + cv] = (unsigned char)bits;
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
@@ -207,7 +221,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
                                                               const float* __restrict__ sums,
                                                               bf16* __restrict__ dy, bf16* __restrict__ dres,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              long long M, int C, int relu, int train) {
+                                                              long long M, int C, int relu, int train,
+                                                              const unsigned char* __restrict__ zmask) {
     const int cvec = C >> 3;
     const int rows_per_iter = 256 / cvec;
     const int cv = threadIdx.x % cvec;
@@ -216,7 +231,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
     // in-flight loads):  dy = ca*d + cb*y + cc  with d = dz masked;  mask (no saved z): cp*y + cq > 0.
     float ca[8], cb[8], cc[8], cp[8], cq[8];
     const float inv_m = 1.f / (float)M;
-    const bool mask_from_y = relu && z == nullptr;
+    const bool use_bits = relu && zmask != nullptr;
+    const bool mask_from_y = relu && z == nullptr && !use_bits;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
@@ -237,10 +253,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
             dgamma[cv * 8 + i] = sums[C + cv * 8 + i];
         }
     }
-    const bool use_z = relu && !mask_from_y;
+    const bool use_z = relu && !mask_from_y && !use_bits;
     const long long rstride = (long long)gridDim.x * rows_per_iter;
     for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < M; r0 += rstride * BN_UNROLL) {
         bf16x8 vd[BN_UNROLL], vy[BN_UNROLL], vz[BN_UNROLL];
+        unsigned int mb[BN_UNROLL];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
             const long long r = r0 + u * rstride;
@@ -249,6 +266,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
                 vd[u] = ld8(dz + off);
                 vy[u] = ld8(y + off);
                 if (use_z) vz[u] = ld8(z + off);
+                if (use_bits) mb[u] = zmask[r * cvec + cv];
             }
         }
 #pragma unroll
@@ -259,7 +277,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
             float d[8], yy[8];
             unpack8(vd[u], d);
             unpack8(vy[u], yy);
-            if (use_z) {
+            if (use_bits) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (!((mb[u] >> i) & 1u)) d[i] = 0.f;
+            } else if (use_z) {
                 float zz[8];
                 unpack8(vz[u], zz);
 #pragma unroll
@@ -507,7 +528,7 @@ extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, vo
     DFU_CHECK_ARG(y && sums && M > 0 && bn_shape_ok(C), "dfu_bn_stats: unsupported shape M=%lld C=%d", (long long)M, C);
     const int rpi = 256 / (C / 8);
     bn_reduce_kernel<0><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
+        (const bf16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0, nullptr);
     DFU_CHECK_LAUNCH("bn_stats");
     return DFU_OK;
 }
@@ -527,18 +548,18 @@ extern "C" int dfu_bn_eval_stats(const float* running_mean, const float* running
     return DFU_OK;
 }
 extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
-                            void* z, int64_t M, int32_t C, int32_t relu, void* stream) {
+                            void* z, uint8_t* zmask, int64_t M, int32_t C, int32_t relu, void* stream) {
     DFU_CHECK_ARG(y && mean_invstd && gamma && beta && z && M > 0 && bn_shape_ok(C), "dfu_bn_apply: unsupported shape M=%lld C=%d",
                   (long long)M, C);
     const int rpi = 256 / (C / 8);
     bn_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, nullptr, nullptr,
-        nullptr, nullptr, 0.f, 0.f);
+        nullptr, nullptr, 0.f, 0.f, zmask);
     DFU_CHECK_LAUNCH("bn_apply");
     return DFU_OK;
 }
 extern "C" int dfu_bn_apply_train(const void* y, const float* sums, const float* gamma, const float* beta, const void* res, void* z,
-                                  float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                  uint8_t* zmask, float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                                   int64_t M, int32_t C, int32_t relu, float eps, float momentum, void* stream) {
     DFU_CHECK_ARG(y && sums && gamma && beta && z && mean_invstd && M > 0 && bn_shape_ok(C),
                   "dfu_bn_apply_train: unsupported shape M=%lld C=%d", (long long)M, C);
@@ -546,29 +567,30 @@ extern "C" int dfu_bn_apply_train(const void* y, const float* sums, const float*
     const int rpi = 256 / (C / 8);
     bn_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, sums, running_mean, running_var,
-        (long long*)num_batches_tracked, eps, momentum);
+        (long long*)num_batches_tracked, eps, momentum, zmask);
     DFU_CHECK_LAUNCH("bn_apply_train");
     return DFU_OK;
 }
-extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
-                                 const float* beta, float* sums, int64_t M, int32_t C, int32_t relu, void* stream) {
-    DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z || (gamma && beta)),
+extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const uint8_t* zmask, const void* y, const float* mean_invstd,
+                                 const float* gamma, const float* beta, float* sums, int64_t M, int32_t C, int32_t relu,
+                                 void* stream) {
+    DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z || zmask || (gamma && beta)),
                   "dfu_bn_bwd_reduce: bad args");
     const int rpi = 256 / (C / 8);
     bn_reduce_kernel<1><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu);
+        (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu, zmask);
     DFU_CHECK_LAUNCH("bn_bwd_reduce");
     return DFU_OK;
 }
-extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const uint8_t* zmask, const void* y, const float* mean_invstd, const float* gamma,
                                 const float* beta, const float* sums, void* dy, void* dres, float* dgamma, float* dbeta,
                                 int64_t M, int32_t C, int32_t relu, int32_t train, void* stream) {
-    DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z || beta),
+    DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z || zmask || beta),
                   "dfu_bn_bwd_apply: bad args");
     const int rpi = 256 / (C / 8);
     bn_bwd_apply_kernel<<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta,
-        M, C, relu, train);
+        M, C, relu, train, zmask);
     DFU_CHECK_LAUNCH("bn_bwd_apply");
     return DFU_OK;
 }

@@ -226,20 +226,23 @@ class BatchNormActFn(Function):
         B, H, W, C = yn.shape
         y2 = yn.reshape(B * H * W, C)
         res2 = ops.as_nhwc(res).reshape(B * H * W, C) if res is not None else None
-        z, mi = ops.bn_forward(y2, gamma, beta, running_mean, running_var, nbt, res2, relu, training, eps, momentum,
-                               sums=sums if training else None)
+        need_mask = relu and res is not None and any(ctx.needs_input_grad[:4])
+        out = ops.bn_forward(y2, gamma, beta, running_mean, running_var, nbt, res2, relu, training, eps, momentum,
+                             sums=sums if training else None, want_mask=need_mask)
+        z, mi = out[0], out[1]
         ctx.cfg = (B, H, W, C, relu, training, res is not None)
-        # without a residual input the ReLU mask is recomputed from y in the backward kernels (z is not re-read)
-        ctx.save_for_backward(y2, z if (relu and res is not None) else None, mi, gamma, beta)
+        # ReLU mask for the backward kernels: recomputed from y when there is no residual input, otherwise the 1-bit-
+        # per-element mask the apply kernel wrote (z itself is never re-read)
+        ctx.save_for_backward(y2, out[2] if need_mask else None, mi, gamma, beta)
         return z.view(B, H, W, C).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gz):
-        y2, z, mi, gamma, beta = ctx.saved_tensors
+        y2, zmask, mi, gamma, beta = ctx.saved_tensors
         B, H, W, C, relu, training, has_res = ctx.cfg
         g = ops.as_nhwc(gz).reshape(B * H * W, C)
-        dy, dres, dg, db = ops.bn_backward(g, z, y2, mi, gamma, relu, training, has_res and ctx.needs_input_grad[3],
-                                           beta=beta)
+        dy, dres, dg, db = ops.bn_backward(g, None, y2, mi, gamma, relu, training, has_res and ctx.needs_input_grad[3],
+                                           beta=beta, zmask=zmask)
         dy = dy.view(B, H, W, C).permute(0, 3, 1, 2)
         if dres is not None:
             dres = dres.view(B, H, W, C).permute(0, 3, 1, 2)

@@ -392,10 +392,13 @@ def col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc):
 
 
 # ------------------------------------------------------------------------------------------ BatchNorm
-def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, training, eps, momentum, sums=None):
-    """`sums` ([2C] fp32: per-channel sum and sum of squares of y) may come from the convolution GEMM's epilogue."""
+def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, training, eps, momentum, sums=None,
+               want_mask=False):
+    """`sums` ([2C] fp32: per-channel sum and sum of squares of y) may come from the convolution GEMM's epilogue.
+    want_mask: also return the ReLU mask as 1 bit per element (u8 [M, C/8]) -> (z, mean_invstd, mask)."""
     M, C = y2d.shape
     dev = y2d.device
+    zmask = torch.empty((M, C // 8), dtype=torch.uint8, device=dev) if (want_mask and relu) else None
     mean_invstd = torch.empty(2 * C, dtype=F32, device=dev)
     L = _L()
     z = torch.empty_like(y2d)
@@ -405,16 +408,16 @@ def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, tr
             check(L.dfu_bn_stats(_p(y2d), _p(sums), M, C, _st()), "bn_stats")
             _count()
         # finalize (mean/invstd, running statistics) and apply in one launch
-        check(L.dfu_bn_apply_train(_p(y2d), _p(sums), _p(gamma), _p(beta), _p(res2d), _p(z), _p(mean_invstd),
+        check(L.dfu_bn_apply_train(_p(y2d), _p(sums), _p(gamma), _p(beta), _p(res2d), _p(z), _p(zmask), _p(mean_invstd),
                                    _p(running_mean), _p(running_var), _p(nbt), M, C, 1 if relu else 0, eps, momentum,
                                    _st()), "bn_apply_train")
         _count()
-        return z, mean_invstd
+        return (z, mean_invstd, zmask) if want_mask else (z, mean_invstd)
     check(L.dfu_bn_eval_stats(_p(running_mean), _p(running_var), _p(mean_invstd), C, eps, _st()), "bn_eval_stats")
-    check(L.dfu_bn_apply(_p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(res2d), _p(z), M, C, 1 if relu else 0,
-                         _st()), "bn_apply")
+    check(L.dfu_bn_apply(_p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(res2d), _p(z), _p(zmask), M, C,
+                         1 if relu else 0, _st()), "bn_apply")
     _count(2)
-    return z, mean_invstd
+    return (z, mean_invstd, zmask) if want_mask else (z, mean_invstd)
 
 
 def bn_stats(y2d):
@@ -426,19 +429,19 @@ def bn_stats(y2d):
     return sums
 
 
-def bn_backward(dz2d, z2d, y2d, mean_invstd, gamma, relu, training, want_dres, beta=None):
+def bn_backward(dz2d, z2d, y2d, mean_invstd, gamma, relu, training, want_dres, beta=None, zmask=None):
     """z2d may be None for a ReLU block without residual input: the mask is then recomputed from y (needs beta)."""
     M, C = y2d.shape
     dev = y2d.device
     L = _L()
     sums = zeros(2 * C, F32, dev)
-    check(L.dfu_bn_bwd_reduce(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), M, C,
+    check(L.dfu_bn_bwd_reduce(_p(dz2d), _p(z2d), _p(zmask), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), M, C,
                               1 if relu else 0, _st()), "bn_bwd_reduce")
     dy = torch.empty_like(y2d)
     dres = torch.empty_like(y2d) if want_dres else None
     dgamma = torch.empty(C, dtype=F32, device=dev)
     dbeta = torch.empty(C, dtype=F32, device=dev)
-    check(L.dfu_bn_bwd_apply(_p(dz2d), _p(z2d), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), _p(dy), _p(dres),
+    check(L.dfu_bn_bwd_apply(_p(dz2d), _p(z2d), _p(zmask), _p(y2d), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), _p(dy), _p(dres),
                              _p(dgamma), _p(dbeta), M, C, 1 if relu else 0, 1 if training else 0, _st()),
           "bn_bwd_apply")
     _count(2)

@@ -121,21 +121,23 @@ int dfu_bn_finalize(const float* sums, float* mean_invstd, float* running_mean, 
 int dfu_bn_eval_stats(const float* running_mean, const float* running_var, float* mean_invstd, int32_t C,
                       float eps, void* stream);
 /* z = [relu]( gamma*(y-mean)*invstd + beta [+ res] ) */
+/* zmask (may be null; u8 [M, C/8]): bit i of byte (m, c/8) = (z[m, c/8*8+i] > 0) -- the ReLU mask the backward pass needs
+ * when the block has a residual input, 1 bit per element instead of re-reading z. */
 int dfu_bn_apply(const void* y, const float* mean_invstd, const float* gamma, const float* beta, const void* res,
-                 void* z, int64_t M, int32_t C, int32_t relu, void* stream);
+                 void* z, uint8_t* zmask, int64_t M, int32_t C, int32_t relu, void* stream);
 /* train(): dfu_bn_finalize and dfu_bn_apply in one launch -- mean/invstd from the batch sums (stored to mean_invstd for the
  * backward pass), running statistics and num_batches_tracked updated, then z = [relu](gamma*xhat + beta [+ res]). */
 int dfu_bn_apply_train(const void* y, const float* sums, const float* gamma, const float* beta, const void* res, void* z,
-                       float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       uint8_t* zmask, float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                        int64_t M, int32_t C, int32_t relu, float eps, float momentum, void* stream);
 /* Backward pass 1: sums[0:C] += sum(dpre), sums[C:2C] += sum(dpre*xhat), dpre = dz*(z>0 if relu).
- * z may be null when the block had no residual input: the mask is then recomputed from y as gamma*xhat+beta > 0
+ * The ReLU mask comes from zmask (see dfu_bn_apply) when given, else from z; both may be null when the block had no residual input: the mask is then recomputed from y as gamma*xhat+beta > 0
  * (gamma, beta required), which saves reading z. */
-int dfu_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
-                      const float* beta, float* sums, int64_t M, int32_t C, int32_t relu, void* stream);
+int dfu_bn_bwd_reduce(const void* dz, const void* z, const uint8_t* zmask, const void* y, const float* mean_invstd,
+                      const float* gamma, const float* beta, float* sums, int64_t M, int32_t C, int32_t relu, void* stream);
 /* Backward pass 2: dy = gamma*invstd*(dpre - sum_dpre/M - xhat*sum_dpre_xhat/M); dres = dpre (optional);
  * train=0 (eval BN): dy = gamma*invstd*dpre. dgamma/dbeta (fp32 [C]) written when non-null. */
-int dfu_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean_invstd, const float* gamma,
+int dfu_bn_bwd_apply(const void* dz, const void* z, const uint8_t* zmask, const void* y, const float* mean_invstd, const float* gamma,
                      const float* beta, const float* sums, void* dy, void* dres, float* dgamma, float* dbeta, int64_t M,
                      int32_t C, int32_t relu, int32_t train, void* stream);
 

@@ -308,6 +308,17 @@ def test_batchnorm_train_eval_backward(ops, dev, C, M):
         close(dg3, g3.grad, 1e-3, 1e-3)
         close(db3, b3.grad, 1e-3, 1e-3)
         close(dy3, dy3z, 3 * BF16_EPS, 2e-3)                # mask-from-y agrees with mask-from-z
+        # residual block: the forward pass can hand the mask over as 1 bit per element instead of z
+        z4, mi4, zm = ops.bn_forward(y, gamma, beta, rm.clone(), rv.clone(), nbt.clone(), res, True, True, 1e-5, 0.1,
+                                     want_mask=True)
+        assert zm.shape == (M, C // 8)
+        close(z4, z, 2 * BF16_EPS, 1e-3)                      # (the batch sums are accumulated atomically: order varies)
+        bits = ((zm.long().unsqueeze(-1) >> torch.arange(8, device=dev)) & 1).reshape(M, C).bool()
+        assert torch.equal(bits, z4 > 0)                      # the mask is exactly the sign pattern of the stored output
+        dy4, dres4, dg4, db4 = ops.bn_backward(dz, None, y, mi4, gamma, True, True, True, zmask=zm)
+        assert torch.equal(dres4, torch.where(bits, dz, torch.zeros_like(dz)))
+        close(dy4, dy, 3 * BF16_EPS, 2e-3)
+        close(dg4, dg, 1e-3, 1e-3)
     rm.normal_(0, 0.1)
     rv.uniform_(0.5, 1.5)
     z2, _ = ops.bn_forward(y, gamma, beta, rm, rv, nbt, None, False, False, 1e-5, 0.1)
