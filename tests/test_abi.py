@@ -41,6 +41,22 @@ def test_gemm_args_struct_matches_header_layout():
     assert ctypes.sizeof(_lib.AdamWTensor) == 48
 
 
+def test_conv_args_struct_matches_header_layout():
+    import re
+    with open(_lib.HEADER) as f:
+        text = f.read()
+    body = re.search(r"typedef struct \{([^}]*)\} dfu_conv_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(part.replace("*", " ").split()[-1])
+    assert names == [f[0] for f in _lib.ConvArgs._fields_]
+
+
 def test_sass_has_blackwell_tensor_and_tma_instructions():
     exe = "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(exe):
@@ -49,6 +65,9 @@ def test_sass_has_blackwell_tensor_and_tma_instructions():
     assert "UTCHMMA" in out, "tcgen05.mma missing from SASS"
     assert "UTMALDG" in out and "UTMASTG" in out, "TMA load/store missing from SASS"
     assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "UTCHMMA.2CTA" in out and "UTMALDG.4D.2CTA" in out and "UTCBAR.2CTA.MULTICAST" in out, \
+        "cta_group::2 (CTA-pair) GEMM path missing from SASS"
+    assert "UTMAREDG" in out, "TMA reduce-add (split-K) missing from SASS"
     assert "HMMA." not in out.replace("UTCHMMA", ""), "legacy mma.sync path present"
 
 

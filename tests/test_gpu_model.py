@@ -177,6 +177,44 @@ def test_loss_curve_tracks_oracle(R, D, dev):
         assert abs(a - b) / b < 0.05, (lc, lo)
 
 
+def test_loss_curve_200_steps_against_golden(R, D, dev, golden_dir):
+    """north_star: loss curves within 1 % over 200 steps.  The oracle side (200 fp32 CPU steps, ~10 min) is the committed
+    fixture tests/golden/loss_curve_200_seed1.json written by oracle/make_loss_curve.py; the CUDA path replays the same
+    200 synthetic batches here (CUDA-graph steps)."""
+    import json
+    from dfu_multimodal_b200.optim import FusedAdamW
+    from dfu_multimodal_b200.train import TrainStep
+    path = os.path.join(golden_dir, "loss_curve_200_seed1.json")
+    if not os.path.exists(path):
+        pytest.skip("golden loss curve not generated")
+    with open(path) as f:
+        gold = json.load(f)
+    steps, B = gold["steps"], gold["batch"]
+    oracle = R.seeded_init_(R.OracleFusion(), gold["init_seed"])     # same seeded weights the fixture started from
+    model = D.MultimodalFusionModel()
+    model.load_state_dict(oracle.state_dict())
+    model.to(dev)
+    set_dropout(model, 0.0)
+    w = torch.tensor([276 / 130, 276 / 146]).to(dev)
+    ts = TrainStep(model, FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-4), w, use_graph=True)
+    lc = []
+    for i in range(steps):
+        a, b, y = R.synthetic_batch(B, gold["batch_seed0"] + i)
+        lc.append(ts(a.to(dev), b.to(dev), y.to(dev))[0].item())
+    lo = gold["oracle"]
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/loss_curve_200.json", "w") as f:
+            json.dump({"steps": steps, "batch": B, "cuda": lc, "oracle": lo}, f)
+    except OSError:
+        pass
+    mean_c, mean_o = sum(lc) / steps, sum(lo) / steps
+    assert abs(mean_c - mean_o) / mean_o < 0.01, (mean_c, mean_o)      # the curve over 200 steps: within 1 %
+    for k in range(0, steps, 25):                                      # and every 25-step window of it: within 2 %
+        wc, wo = sum(lc[k:k + 25]) / 25, sum(lo[k:k + 25]) / 25
+        assert abs(wc - wo) / wo < 0.02, (k, wc, wo)
+
+
 def test_cuda_graph_step_equals_eager_step(R, D, dev):
     from dfu_multimodal_b200.optim import FusedAdamW
     from dfu_multimodal_b200.train import TrainStep

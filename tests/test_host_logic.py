@@ -149,3 +149,9 @@ def test_head_builder_variants():
     h2, h3 = make_head(2816, 2, 0.7, 2), make_head(2816, 2, 0.5, 3)
     assert [k for k in h2.state_dict()] == ["0.weight", "0.bias", "3.weight", "3.bias"]
     assert [k for k in h3.state_dict()] == ["0.weight", "0.bias", "3.weight", "3.bias", "6.weight", "6.bias"]
+
+
+def test_device_prefetcher_has_no_cpu_path():
+    from dfu_multimodal_b200.data import DevicePrefetcher
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher(iter([]), "cpu")
