@@ -226,9 +226,25 @@ def main():
     loss_val = 0.0
     # every step's inputs come from pinned HOST memory (H2D inside the timed region, issued one step ahead on a copy
     # stream by the package's DevicePrefetcher) and every step's loss is read back to the host (D2H + sync)
-    for db in DevicePrefetcher((host[i % 2] for i in range(e2e_steps)), dev):
+    # ... through a pinned 4-byte buffer: the copy is enqueued right behind the step and its value is taken one step later,
+    # so reading the result does not drain the launch queue (the reference's per-step .item(), :383, does)
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [None, None]
+    n_read = 0
+    for i, db in enumerate(DevicePrefetcher((host[j % 2] for j in range(e2e_steps)), dev)):
         loss, _ = ts(*db)
-        loss_val = float(loss.item())
+        loss_host[i % 2].copy_(loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        loss_ready[i % 2] = ev
+        if i > 0:
+            loss_ready[(i - 1) % 2].synchronize()
+            loss_val = float(loss_host[(i - 1) % 2])
+            n_read += 1
+    loss_ready[(e2e_steps - 1) % 2].synchronize()
+    loss_val = float(loss_host[(e2e_steps - 1) % 2])
+    n_read += 1
+    assert n_read == e2e_steps
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
