@@ -140,4 +140,24 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// gelu(x) and d/dx gelu(x) together (shared polynomial and reciprocal): g = gelu_fast(x), d = gelu_grad_fast(x).
+__device__ __forceinline__ void gelu_both_fast(float x, float& g, float& d) {
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
+    float q = 0.0000430638f;
+    q = fmaf(q, z, 0.0002765672f);
+    q = fmaf(q, z, 0.0001520143f);
+    q = fmaf(q, z, 0.0092705272f);
+    q = fmaf(q, z, 0.0422820123f);
+    q = fmaf(q, z, 0.0705230784f);
+    q = fmaf(q, z, 1.0f);
+    q = q * q; q = q * q; q = q * q; q = q * q;
+    float r, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+    g = fmaf(-0.5f * ax, r, fmaxf(x, 0.f));
+    const float cdf = x >= 0.f ? fmaf(-0.5f, r, 1.f) : 0.5f * r;
+    d = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 #endif  // __CUDACC__

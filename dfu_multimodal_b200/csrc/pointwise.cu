@@ -154,7 +154,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if (cv * 8 < N) {
-        for (long long r = r0 + rl; r < r1; r += 8) {
+        long long r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {                 // four independent 16-byte loads in flight per thread
+            bf16x8 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld8(x + (r + 8 * u) * ld + cv * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+        }
+        for (; r < r1; r += 8) {
             float f[8];
             unpack8(ld8(x + r * ld + cv * 8), f);
 #pragma unroll

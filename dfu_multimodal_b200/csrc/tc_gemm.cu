@@ -437,19 +437,45 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         constexpr bool GEN = (EM == 0);
         const bool f_tma = GEN ? (p.tma_store != 0) : true;
         const bool f_fp32 = GEN ? (p.d_fp32 != 0) : (EM == 5);
-        const bool f_bias = GEN ? (p.bias != nullptr) : (EM >= 2 && EM <= 4);
-        const int f_act = GEN ? p.act : (EM == 4 ? 2 : 0);
-        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3);
-        const bool f_aux = GEN ? (p.aux != nullptr) : (EM == 4);
+        const bool f_bias = GEN ? (p.bias != nullptr) : ((EM >= 2 && EM <= 4) || EM == 7);
+        const int f_act = GEN ? p.act : (EM == 4 ? 2 : EM == 6 ? 5 : EM == 7 ? 4 : 0);
+        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3 || EM == 6);
+        const bool f_aux = GEN ? (p.aux != nullptr) : (EM == 4 || EM == 7);
         const float alpha = GEN ? p.alpha : 1.f;
         const int quarter = warp_idx & 3;        // TMEM lane quarter this warp may touch
         const int group = ew >> 2;               // two warps share a quarter, alternate 32-column chunks
         const int n_chunks = p.block_n / 32;
+        // column statistics: each lane keeps (sum, sum of squares) of its two columns of the warp's two slabs of the
+        // current column tile in registers across work items; they go to the CTA's shared accumulators only when the
+        // column tile changes (the host sizes the grid so that it rarely does) -- shared float atomics are CAS loops
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int cs_tile = -1;
+        float* const cs_acc = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * (f_aux ? 2 : 1) * STG_BYTES);
+        auto cs_flush = [&]() {
+            if (cs_tile < 0) return;
+#pragma unroll
+            for (int ai = 0; ai < 2; ++ai) {
+                const int col = cs_tile * p.block_n + (group + 2 * ai) * 64 + 2 * lane;
+                if ((group + 2 * ai) * 64 < p.block_n) {
+                    if (col < p.N) {
+                        atomicAdd(cs_acc + col, cs[ai * 4]);
+                        if (p.colstats_mode == 2) atomicAdd(cs_acc + p.N + col, cs[ai * 4 + 2]);
+                    }
+                    if (col + 1 < p.N) {
+                        atomicAdd(cs_acc + col + 1, cs[ai * 4 + 1]);
+                        if (p.colstats_mode == 2) atomicAdd(cs_acc + p.N + col + 1, cs[ai * 4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+        };
         int it = 0;
         for (long long w = work0; w < p.total_work; w += work_step, ++it) {
             long long t = w;
             const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
             const int m_tile = (int)(t % p.m_tiles) * CG + (int)cta_rank; t /= p.m_tiles;     // this CTA's 128-row tile
+            if (CS && p.colstats && n_tile != cs_tile) { cs_flush(); cs_tile = n_tile; }
             t /= p.split_k;
             const int z0 = (int)(t % p.nb0);
             const int z1 = (int)(t / p.nb0);
@@ -459,6 +485,19 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tc_fence_after();
             const int m = m_tile * BLOCK_M + quarter * 32 + lane;
             const bool row_ok = m < p.M;
+            uint32_t cs_rows = 0;            // which of this warp's 32 tile rows are samples of the column statistics
+            if (CS && p.colstats) {
+                bool row_in = row_ok;
+                if (p.cv_mode) {
+                    // a tile row outside the image still holds a value (its taps reach inside): not a sample
+                    const int idx = quarter * 32 + lane;
+                    const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
+                    row_in = wt * p.cv_wb + idx % p.cv_wb < p.cv_ow &&
+                             ht * p.cv_hb + (idx / p.cv_wb) % p.cv_hb < p.cv_oh &&
+                             bt * p.cv_bb + idx / (p.cv_wb * p.cv_hb) < p.cv_nb;
+                }
+                cs_rows = __ballot_sync(0xffffffffu, row_in);
+            }
             const long long d_off = (long long)z1 * p.sd1 + (long long)z0 * p.sd0 + (long long)m * p.ldd;
             const long long r_off = (long long)z1 * p.sr1 + (long long)z0 * p.sr0 + (long long)m * p.ldr;
             if (f_tma) {
@@ -470,7 +509,6 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 uint8_t* const stg_base = smem + p.stages * p.stage_bytes + ew * p.epi_bufs * set_bytes;
                 const uint32_t sa_base = smem_u32(stg_base) + lane * 128;
                 int bufsel = 0;
-                float* const colacc = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * set_bytes);
                 const int slab_cols = f_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
@@ -532,7 +570,15 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         const uint32_t rowp = sa_aux;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const bf16x8 pk = pack8(v + q * 8);
+                            bf16x8 pk;
+                            if (f_act == 4) {                // aux = gelu'(pre-activation), v = gelu(pre-activation)
+                                float dv[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) gelu_both_fast(v[q * 8 + j], v[q * 8 + j], dv[j]);
+                                pk = pack8(dv);
+                            } else {
+                                pk = pack8(v + q * 8);
+                            }
                             sts16(rowp + (((ch * 4 + q) ^ (lane & 7)) << 4), &pk);
                         }
                     }
@@ -551,6 +597,9 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             if (f_act == 3) {                // res holds the pre-activation h: D *= gelu'(h)
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[q * 8 + j] *= gelu_grad_fast(rv[j]);
+                            } else if (f_act == 5) {         // res holds the activation derivative: D *= res
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[q * 8 + j] *= rv[j];
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
@@ -578,34 +627,29 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         __syncwarp();
                         const uint32_t sbase = smem_u32(stg_out) + (lane & 3) * 4;
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        if (cs_rows == 0xffffffffu) {
 #pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            bool row_in = row0 + r < p.M;                // warp-uniform
-                            if (p.cv_mode) {
-                                // a tile row outside the image still holds a value (its taps reach inside): not a sample
-                                const int idx = quarter * 32 + r;
-                                const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
-                                row_in = wt * p.cv_wb + idx % p.cv_wb < p.cv_ow &&
-                                         ht * p.cv_hb + (idx / p.cv_wb) % p.cv_hb < p.cv_oh &&
-                                         bt * p.cv_bb + idx / (p.cv_wb * p.cv_hb) < p.cv_nb;
-                            }
-                            if (row_in) {
+                            for (int r = 0; r < 32; ++r) {
                                 uint32_t w;
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+                                asm("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
                                 const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
                                 s0 += f.x; s1 += f.y;
                                 q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
                             }
+                        } else {
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                if ((cs_rows >> r) & 1u) {           // warp-uniform
+                                    uint32_t w;
+                                    asm("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
+                                    s0 += f.x; s1 += f.y;
+                                    q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                                }
+                            }
                         }
-                        const int col = ncol0 + 2 * lane;
-                        if (col < p.N) {
-                            atomicAdd(colacc + col, s0);
-                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col, q0);
-                        }
-                        if (col + 1 < p.N) {
-                            atomicAdd(colacc + col + 1, s1);
-                            if (p.colstats_mode == 2) atomicAdd(colacc + p.N + col + 1, q1);
-                        }
+                        if (((sl >> 1) & 1) == 0) { cs[0] += s0; cs[1] += s1; cs[2] += q0; cs[3] += q1; }
+                        else                      { cs[4] += s0; cs[5] += s1; cs[6] += q0; cs[7] += q1; }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -689,11 +733,17 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (!row_ok) continue;
                     if (p.aux) {
                         bf16* ap = p.aux + d_off + n;
+                        float av[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            av[j] = v[j];
+                            if (p.act == 4) gelu_both_fast(v[j], v[j], av[j]);
+                        }
                         if (full8 && p.vec_ok) {
-                            st8(ap, pack8(v));
+                            st8(ap, pack8(av));
                         } else {
                             for (int j = 0; j < 8; ++j)
-                                if (n + j < p.N) ap[j] = __float2bfloat16(v[j]);
+                                if (n + j < p.N) ap[j] = __float2bfloat16(av[j]);
                         }
                     }
                     if (p.act == 1) {
@@ -714,6 +764,9 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         if (p.act == 3) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(rv[j]);
+                        } else if (p.act == 5) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] *= rv[j];
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += rv[j];
@@ -762,6 +815,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (CG == 2) mbar_arrive_cta(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]);
             }
         }
+        if (CS && p.colstats) cs_flush();
         if (f_tma && lane == 0) bulk_wait0();   // all bulk stores of this warp have completed
     }
 
@@ -830,12 +884,12 @@ __global__ void __launch_bounds__(256) dfu_ref_gemm_kernel(const RefParams p) {
     float v = acc * p.alpha;
     if (p.bias) v += p.bias[n];
     const long long d_off = z1 * p.sd1 + z0 * p.sd0 + (long long)m * p.ldd + n;
-    if (p.aux) p.aux[d_off] = __float2bfloat16(v);
+    if (p.aux) p.aux[d_off] = __float2bfloat16(p.act == 4 ? gelu_erf_grad(v) : v);
     if (p.act == 1) v = fmaxf(v, 0.f);
-    else if (p.act == 2) v = gelu_erf(v);
+    else if (p.act == 2 || p.act == 4) v = gelu_erf(v);
     if (p.res) {
         const float rv = __bfloat162float(p.res[z1 * p.sr1 + z0 * p.sr0 + (long long)m * p.ldr + n]);
-        if (p.act == 3) v *= gelu_erf_grad(rv); else v += rv;
+        if (p.act == 3) v *= gelu_erf_grad(rv); else if (p.act == 5) v *= rv; else v += rv;
     }
     if (p.d_fp32) {
         float* d = reinterpret_cast<float*>(p.D) + d_off;
@@ -959,14 +1013,21 @@ cudaError_t set_smem_attrs() {
     DFU_SET_ATTR(false, 3, 1); DFU_SET_ATTR(false, 4, 1); DFU_SET_ATTR(false, 5, 1);
     DFU_SET_ATTR(false, 1, 2); DFU_SET_ATTR(false, 2, 2); DFU_SET_ATTR(false, 3, 2); DFU_SET_ATTR(false, 4, 2);
     DFU_SET_ATTR(false, 5, 2);
+    DFU_SET_ATTR(false, 6, 1); DFU_SET_ATTR(false, 6, 2); DFU_SET_ATTR(true, 6, 1); DFU_SET_ATTR(true, 6, 2);
+    DFU_SET_ATTR(false, 7, 1); DFU_SET_ATTR(false, 7, 2);
 #undef DFU_SET_ATTR
     return e;
 }
 
 // Which epilogue instantiation serves this launch (-1: the one with the column-statistics code).
 int pick_epilogue_mode(const GemmParams& p) {
-    if (p.colstats)      // -1: general epilogue + column statistics; -2: plain bf16 store + column statistics
-        return (p.tma_store && p.alpha == 1.f && !p.d_fp32 && !p.bias && !p.res && !p.aux && p.act == 0) ? -2 : -1;
+    if (p.colstats) {    // -1: general epilogue + column statistics; -2: plain bf16 store; -6: bf16 (x) res
+        if (p.tma_store && p.alpha == 1.f && !p.d_fp32 && !p.bias && !p.aux) {
+            if (!p.res && p.act == 0) return -2;
+            if (p.res && p.act == 5) return -6;
+        }
+        return -1;
+    }
     if (!p.tma_store || p.alpha != 1.f) return 0;
     const bool bias = p.bias != nullptr, res = p.res != nullptr, aux = p.aux != nullptr;
     if (p.d_fp32) return (!bias && !res && !aux && p.act == 0) ? 5 : 0;
@@ -974,10 +1035,12 @@ int pick_epilogue_mode(const GemmParams& p) {
     if (bias && !res && !aux && p.act == 0) return 2;
     if (bias && res && !aux && p.act == 0) return 3;
     if (bias && !res && aux && p.act == 2) return 4;
+    if (!bias && res && !aux && p.act == 5) return 6;
+    if (bias && !res && aux && p.act == 4) return 7;
     return 0;
 }
 
-template <int EM>
+template <int EM, bool CS = false>
 void launch_pair(int grid, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
                  const CUtensorMap& mx, const GemmParams& p) {
     cudaLaunchConfig_t cfg;
@@ -993,7 +1056,7 @@ void launch_pair(int grid, cudaStream_t stream, const CUtensorMap& ma, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    (void)cudaLaunchKernelEx(&cfg, dfu_tc_gemm_kernel<false, EM, 2>, ma, mb, md, mx, p);
+    (void)cudaLaunchKernelEx(&cfg, dfu_tc_gemm_kernel<CS, EM, 2>, ma, mb, md, mx, p);
 }
 
 void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
@@ -1004,6 +1067,9 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
             case 2: launch_pair<2>(grid, stream, ma, mb, md, mx, p); return;
             case 3: launch_pair<3>(grid, stream, ma, mb, md, mx, p); return;
             case 4: launch_pair<4>(grid, stream, ma, mb, md, mx, p); return;
+            case 6: launch_pair<6>(grid, stream, ma, mb, md, mx, p); return;
+            case -6: launch_pair<6, true>(grid, stream, ma, mb, md, mx, p); return;
+            case 7: launch_pair<7>(grid, stream, ma, mb, md, mx, p); return;
             default: launch_pair<5>(grid, stream, ma, mb, md, mx, p); return;
         }
     }
@@ -1015,6 +1081,9 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
         case 3: dfu_tc_gemm_kernel<false, 3, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 4: dfu_tc_gemm_kernel<false, 4, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 5: dfu_tc_gemm_kernel<false, 5, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 6: dfu_tc_gemm_kernel<false, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case -6: dfu_tc_gemm_kernel<true, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 7: dfu_tc_gemm_kernel<false, 7, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         default: dfu_tc_gemm_kernel<false, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
     }
 }
@@ -1030,10 +1099,11 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     DFU_CHECK_ARG(!(a->accumulate && a->d_dtype != 1), "dfu_gemm: accumulate needs fp32 output");
     DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias || a->colstats)),
                   "dfu_gemm: accumulate mode takes no bias/act/res/aux/colstats");
-    DFU_CHECK_ARG(a->act >= 0 && a->act <= 3 && !(a->act == 3 && !a->res), "dfu_gemm: act=%d (3 needs res = pre-activation)", a->act);
-    DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && a->N <= 2048 && a->nb0 * a->nb1 == 1 &&
-                                   a->d_dtype == 0),
-                  "dfu_gemm: colstats needs mode 1|2, N <= 2048, a bf16 output and no batching");
+    DFU_CHECK_ARG(a->act >= 0 && a->act <= 5 && !((a->act == 3 || a->act == 5) && !a->res) && !(a->act == 4 && !a->aux),
+                  "dfu_gemm: act=%d (3 and 5 need res, 4 needs aux)", a->act);
+    DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && (long long)a->N * a->colstats_mode <= 4096 &&
+                                   a->nb0 * a->nb1 == 1 && a->d_dtype == 0),
+                  "dfu_gemm: colstats needs mode 1|2, N x mode <= 4096, a bf16 output and no batching");
 
     const bool batched = (a->nb0 * a->nb1) > 1;
     bool tma_ok = aligned16(a->A) && aligned16(a->B) && (a->lda % 8 == 0) && (a->ldb % 8 == 0);
@@ -1096,7 +1166,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         probe.tma_store = p.tma_store; probe.alpha = a->alpha; probe.bias = a->bias; probe.res = (const bf16*)a->res;
         probe.aux = (bf16*)a->aux; probe.act = a->act; probe.d_fp32 = a->d_dtype; probe.colstats = a->colstats;
         const int em = pick_epilogue_mode(probe);
-        if (g_pair_enabled && em >= 1 && !batched && p.block_n == 256 && a->N % 256 == 0 && a->M >= 512 && a->K >= 256 &&
+        if (g_pair_enabled && (em >= 1 || em == -6) && !batched && p.block_n == 256 && a->N % 256 == 0 && a->M >= 512 && a->K >= 256 &&
             a->max_ctas == 0) {
             // a pair finishes a 256-row tile in ~0.88 of the time two CTAs need for two 128-row tiles (measured), but it
             // also halves the number of schedulable units: take it only when the wave count does not eat the gain
@@ -1111,7 +1181,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     if (p.cg == 2) {
         // per CTA and stage: 128 x 64 of A + 128 x 64 of B = 32 KB -> 6 stages (5 next to the 64 KB aux staging)
         p.stage_bytes = A_TILE_BYTES + (p.block_n / 2) * BLOCK_K * 2;
-        p.stages = a->aux ? 5 : 6;
+        p.stages = (a->aux || a->colstats) ? 5 : 6;       // 5 x 32 KB next to 64 KB of aux staging / 32 KB + accumulators
         p.epi_bufs = 1;
     }
     p.m_tiles = dfu_cdiv(a->M, BLOCK_M * p.cg);
@@ -1166,7 +1236,11 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         }
         g_attr_set = true;
     }
-    const int grid = p.cg * (int)min((long long)(max_ctas / p.cg), p.total_work);
+    int units = (int)min((long long)(max_ctas / p.cg), p.total_work);
+    // column statistics live in registers while a CTA stays on one column tile: with the column tile the fastest-varying
+    // index of the work order that holds for the whole launch when the number of CTAs is a multiple of n_tiles
+    if (p.colstats && p.n_tiles > 1 && units > p.n_tiles) units -= units % p.n_tiles;
+    const int grid = p.cg * units;
     launch_gemm(pick_epilogue_mode(p), grid, stream, map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel");
     return DFU_OK;
@@ -1296,7 +1370,8 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         }
         g_attr_set = true;
     }
-    const int grid = (int)min((long long)max_ctas, p.total_work);
+    int grid = (int)min((long long)max_ctas, p.total_work);
+    if (p.colstats && p.n_tiles > 1 && grid > p.n_tiles) grid -= grid % p.n_tiles;     // see dfu_gemm
     launch_gemm(pick_epilogue_mode(p), grid, stream, map_a, map_b, map_d, map_x, p);
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel(conv)");
     return DFU_OK;

@@ -14,6 +14,11 @@ from .ops import BF16, F32
 # Epilogue fusions that are implemented and parity-tested but lose on B200 at the benchmark shapes because the GEMMs
 # they attach to are epilogue-bound (small K): measured numbers in profiles/r01e_gemm_bench_isolated.txt.
 FUSE_GELU_BWD = os.environ.get("DFU_FUSE_GELU_BWD", "0") == "1"     # GELU' in the fc2-dgrad epilogue (act=3)
+# fc1's epilogue stores gelu'(h) instead of h; the fc2-dgrad epilogue multiplies by it (act=5) and sums fc1's bias gradient
+GELU_GRAD_AUX = os.environ.get("DFU_GELU_GRAD_AUX", "1") == "1"
+# measured on B200 (profiles/r01o): the act=5 fc2-dgrad GEMM takes 126 us alone and 139 us with the column sums kept in
+# its epilogue's registers; a separate colsum pass over its output takes ~35 us
+FUSE_DGELU_COLSUM = os.environ.get("DFU_FUSE_DGELU_COLSUM", "1") == "1"
 FUSE_BN_STATS = os.environ.get("DFU_FUSE_BN_STATS", "1") == "1"     # BatchNorm sums in the conv GEMM epilogue (colstats)
 FUSE_SKIP_DGRAD = os.environ.get("DFU_FUSE_SKIP_DGRAD", "0") == "1"  # skip-connection gradient in the conv1 dgrad epilogue
 
@@ -392,9 +397,9 @@ class LinearFn(Function):
 
 class MlpFn(Function):
     """timm Mlp (fc1 -> GELU -> fc2) plus the residual add, as one autograd node.  Forward: GELU and the pre-activation
-    copy come out of the fc1 GEMM epilogue, the residual goes into the fc2 epilogue.  Backward: the GELU derivative is
-    applied in the epilogue of the fc2 dgrad GEMM (act=3) which also accumulates fc1's bias gradient (colstats), so no
-    elementwise pass runs between the five GEMMs."""
+    derivative (act=4: aux = gelu'(h), bf16) come out of the fc1 GEMM epilogue, the residual goes into the fc2 epilogue.
+    Backward: the fc2 dgrad epilogue multiplies by the stored derivative (act=5) and accumulates fc1's bias gradient
+    (colstats), so no elementwise pass runs between the five GEMMs."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, res):
@@ -403,7 +408,8 @@ class MlpFn(Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         need_grad = any(ctx.needs_input_grad[:5])
-        a, h = ops.linear_forward(x2, shadow(w1, Hd, D), b1, act=2, want_aux=need_grad)
+        ctx.grad_aux = GELU_GRAD_AUX and need_grad
+        a, h = ops.linear_forward(x2, shadow(w1, Hd, D), b1, act=4 if ctx.grad_aux else 2, want_aux=need_grad)
         res2 = res.reshape(-1, D) if res is not None else None
         y, _ = ops.linear_forward(a, shadow(w2, D, Hd), b2, 0, res2)
         ctx.has_res = res is not None
@@ -417,9 +423,11 @@ class MlpFn(Function):
         g2 = _as_bf16_2d(gy, D)
         dw2 = ops.linear_wgrad(g2, a, Hd).reshape(w2.shape) if ctx.needs_input_grad[3] else None
         db2 = ops.colsum(g2) if ctx.needs_input_grad[4] else None
-        if FUSE_GELU_BWD:
-            db1 = ops.zeros(Hd, F32, g2.device) if (ctx.needs_input_grad[2] and ops.colstats_ok(Hd)) else None
-            dh = ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd, res=h, act=3, colstats=db1)
+        if ctx.grad_aux or FUSE_GELU_BWD:
+            # h holds gelu'(pre-activation) when the forward ran with act=4, the pre-activation itself otherwise
+            db1 = ops.zeros(Hd, F32, g2.device) if (ctx.needs_input_grad[2] and ops.colstats_ok(Hd, mode=1) and
+                                                    (FUSE_DGELU_COLSUM or not ctx.grad_aux)) else None
+            dh = ops.linear_dgrad(g2, shadow(w2, D, Hd), Hd, res=h, act=5 if ctx.grad_aux else 3, colstats=db1)
             if db1 is None and ctx.needs_input_grad[2]:
                 db1 = ops.colsum(dh)
         else:

@@ -178,9 +178,10 @@ def _wgrad_needs_splitk(M, N):
     return tiles < 148
 
 
-def colstats_ok(N, out_dtype=BF16):
-    """The GEMM epilogue can accumulate per-column sums when the output rows are 16-byte aligned and N <= 2048."""
-    return N <= 2048 and (N * (2 if out_dtype == BF16 else 4)) % 16 == 0 and N >= 16
+def colstats_ok(N, out_dtype=BF16, mode=2):
+    """The GEMM epilogue can accumulate per-column sums when the output rows are 16-byte aligned and the CTA-local
+    accumulators (N x mode floats) fit next to the operand ring (<= 4096)."""
+    return N * mode <= 4096 and (N * (2 if out_dtype == BF16 else 4)) % 16 == 0 and N >= 16
 
 
 def linear_forward(x2d, w, bias=None, act=0, res=None, want_aux=False, out_dtype=BF16, colstats=None, colstats_mode=0):
@@ -198,6 +199,7 @@ def linear_forward(x2d, w, bias=None, act=0, res=None, want_aux=False, out_dtype
 def linear_dgrad(dy2d, w, K, res=None, act=0, colstats=None):
     """dx[M,K] = dy2d[M,N] @ w[N,:K] (+ res)  (w row-major [N, ldw]: MN-major B operand).
     act=3: dx = (dy2d @ w) * gelu'(res) -- the GELU backward fused into the dgrad epilogue (res = pre-activation);
+    act=5: dx = (dy2d @ w) * res -- same with the derivative already stored by the forward GEMM (its act=4 aux output);
     colstats ([K] fp32, zeroed) += column sums of dx (the bias gradient of the layer below)."""
     M, N = dy2d.shape
     dx = torch.empty((M, K), dtype=BF16, device=dy2d.device)

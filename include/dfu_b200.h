@@ -42,8 +42,10 @@ int dfu_set_sm_budget(int32_t n_sms);
  *   d_dtype: 0 = bf16, 1 = fp32.  accumulate=1 (fp32 only): D += result (atomic, enables split-K).
  *   aux (bf16, same geometry as D) receives the pre-activation value when non-null.
  *   act: 0 none, 1 relu, 2 gelu(erf), 3 = D = (alpha*acc + bias) * gelu'(res) (res holds the pre-activation; fuses the
- *   GELU backward into the dgrad GEMM).  impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
- *   colstats (fp32, caller zeroes; tcgen05 kernel only, bf16 output, N <= 2048, unbatched): += per-column sums of the
+ *   GELU backward into the dgrad GEMM); 4 = gelu(erf) with aux receiving gelu'(pre-activation) instead of the
+ *   pre-activation (aux required); 5 = D = (alpha*acc + bias) * res (res = the derivative stored by a forward act=4).
+ *   impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
+ *   colstats (fp32, caller zeroes; tcgen05 kernel only, bf16 output, N x mode <= 4096, unbatched): += per-column sums of the
  *   stored (bf16-rounded) D over the M rows
  *   (mode 1: sums[N]) and sums of squares (mode 2: sums[N], sumsq[N]) -- BatchNorm batch statistics straight from the
  *   convolution GEMM, bias gradients straight from the dgrad GEMM.

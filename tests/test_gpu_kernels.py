@@ -103,11 +103,41 @@ def test_gemm_gelu_grad_epilogue(ops, dev, M, N, K, impl):
     close(D, (A.float() @ B.float()) * hf.grad, 2 * BF16_EPS, 2e-3)
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K", [(25216, 3072, 768), (1000, 3072, 768), (333, 200, 96), (64, 64, 64)])
+def test_gemm_stored_gelu_derivative_pair(ops, dev, M, N, K, impl):
+    """act=4 (forward: D = gelu(AB^T + b), aux = gelu'(AB^T + b)) and act=5 (backward: D = (G W) * aux, column sums of
+    D accumulated on the way) -- the fc1 / fc2-dgrad pair of the ViT MLP."""
+    if impl == 1 and M > 5000:
+        pytest.skip("SIMT check kernel: small shapes only")
+    A, W, b = rnd(dev, M, K), rnd(dev, N, K, scale=0.1), torch.randn(N, device=dev) * 0.5
+    D = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    aux = torch.empty_like(D)
+    ops.gemm(A, W, D, M=M, N=N, K=K, lda=K, ldb=K, ldd=N, bias=b, act=4, aux=aux, impl=impl)
+    pre = (A.float() @ W.float().t() + b).requires_grad_(True)
+    ref = F.gelu(pre)
+    ref.sum().backward()
+    close(D, ref, 2 * BF16_EPS, 2e-3)
+    close(aux, pre.grad, 2 * BF16_EPS, 2e-3)
+    # backward: G [M, K2] @ W2 [K2, N] (MN-major B) times the stored derivative, with column sums
+    K2 = 96 if M < 5000 else 768
+    G, W2 = rnd(dev, M, K2), rnd(dev, K2, N, scale=0.1)
+    dh = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    for with_stats in ([False, True] if (impl == 0 and ops.colstats_ok(N, mode=1)) else [False]):
+        st = torch.zeros(N, dtype=torch.float32, device=dev) if with_stats else None
+        dh.zero_()
+        ops.gemm(G, W2, dh, M=M, N=N, K=K2, lda=K2, ldb=N, ldd=N, b_major=1, res=aux, ldr=N, act=5, impl=impl,
+                 colstats=st, colstats_mode=1 if with_stats else 0)
+        close(dh, (G.float() @ W2.float()) * aux.float(), 2 * BF16_EPS, 2e-3)
+        if with_stats:
+            close(st, dh.float().sum(0), 1e-4, 2e-3 * (M ** 0.5))
+
+
 @pytest.mark.parametrize("M,N,K,mode,bias", [(5000, 256, 64, 2, 0), (777, 2048, 512, 2, 0), (1000, 3072, 768, 1, 0),
                                              (300, 64, 147 + 5, 2, 0), (130, 200, 96, 1, 1)])
 def test_gemm_column_statistics_epilogue(ops, dev, M, N, K, mode, bias):
     """colstats: per-column sum (and sum of squares) of the stored results, accumulated by the epilogue."""
-    if not ops.colstats_ok(N):
+    if not ops.colstats_ok(N, mode=mode):
         pytest.skip("N outside the epilogue reduction's range")
     A, B = rnd(dev, M, K), rnd(dev, N, K)
     bias_t = torch.randn(N, device=dev) if bias else None

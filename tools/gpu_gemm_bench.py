@@ -50,6 +50,9 @@ def bench(name, M, N, K, a_major=0, b_major=0, fp32=False, acc=False, bias=False
 
 
 CASES = [
+    ("vit.fc1 fwd gelu+dgelu aux", dict(M=25216, N=3072, K=768, bias=True, act=4, aux=True)),
+    ("vit.fc2 dgrad *res", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=5)),
+    ("vit.fc2 dgrad *res +colsum", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=5, colstats=1)),
     ("vit.fc2 dgrad +gelu'", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=3)),
     ("vit.fc2 dgrad +gelu' +colsum", dict(M=25216, N=3072, K=768, b_major=1, res=True, act=3, colstats=1)),
     ("vit.fc2 dgrad +colsum", dict(M=25216, N=3072, K=768, b_major=1, colstats=1)),
