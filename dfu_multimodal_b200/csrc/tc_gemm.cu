@@ -24,7 +24,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int MAX_BLOCK_N = 256;
-constexpr int MAX_STAGES = 6;         // barrier array size (cta_group::2 runs 6 x 32 KB stages)
+constexpr int MAX_STAGES = 8;         // barrier array size (narrow column tiles run up to 8 x 24 KB stages)
 constexpr int STAGES = 4;            // ring depth (3 when a second staging slab per epilogue warp is needed for aux)
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_TILE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;    // 32 KB
@@ -65,6 +65,7 @@ struct GemmParams {
     int cv_mode;              // 0 plain GEMM, 1 forward, 2 dgrad (stride 1), 3 wgrad
     int cv_wb, cv_hb, cv_bb;  // pixel box of one tile (128 output pixels, or 64 pixels per k-block for wgrad)
     int cv_tw, cv_th;         // boxes per image row / column
+    int cv_lw, cv_lh;         // log2(cv_wb), log2(cv_hb): the box sides are powers of two
     int cv_S, cv_pad;         // filter width, padding
     int cv_cchunks;           // 64-channel chunks of the gathered tensor (fwd: Cin/64, dgrad: Cout/64)
     int cv_C;                 // channels of the tap-major weight columns (Cin)
@@ -246,6 +247,25 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 // CG: 1 = one CTA per 128-row tile; 2 = a CTA pair (cluster of 2) shares a 256-row tile: tcgen05.mma.cta_group::2 issued by
 //     the even CTA, each CTA staging its 128 rows of A and HALF of the B tile, so every SM pulls a third less operand data
 //     per FLOP through its L2 port -- the limit of the 128x256 single-CTA kernel on the K >= 768 shapes.
+// Work item -> (n_tile, m_tile, k split, z0, z1), n_tile fastest.  32-bit arithmetic, and no division at all for the
+// factors that are 1 (the decode runs once per tile in every role; 64-bit runtime divisions were ~15% of the epilogue
+// instructions of the short-K shapes).
+struct WorkItem { int n_tile, m_tile, ks, z0, z1; };
+__device__ __forceinline__ WorkItem decode_work(uint32_t w, const GemmParams& p) {
+    WorkItem o;
+    uint32_t t = w;
+    if (p.n_tiles == 1) { o.n_tile = 0; } else { o.n_tile = (int)(t % (uint32_t)p.n_tiles); t /= (uint32_t)p.n_tiles; }
+    if (p.split_k == 1 && p.nb0 == 1 && p.nb1 == 1) {
+        o.m_tile = (int)t; o.ks = 0; o.z0 = 0; o.z1 = 0;
+        return o;
+    }
+    o.m_tile = (int)(t % (uint32_t)p.m_tiles); t /= (uint32_t)p.m_tiles;
+    o.ks = (int)(t % (uint32_t)p.split_k); t /= (uint32_t)p.split_k;
+    o.z0 = (int)(t % (uint32_t)p.nb0);
+    o.z1 = (int)(t / (uint32_t)p.nb0);
+    return o;
+}
+
 template <bool CS, int EM, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -314,16 +334,21 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // ------------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (long long w = work0; w < p.total_work; w += work_step) {
-                long long t = w;
-                const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
-                const int m_tile = (int)(t % p.m_tiles); t /= p.m_tiles;
-                const int ks = (int)(t % p.split_k); t /= p.split_k;
-                const int z0 = (int)(t % p.nb0);
-                const int z1 = (int)(t / p.nb0);
+            for (uint32_t w = work0; w < (uint32_t)p.total_work; w += work_step) {
+                const WorkItem wi = decode_work(w, p);
+                const int n_tile = wi.n_tile, m_tile = wi.m_tile, ks = wi.ks, z0 = wi.z0, z1 = wi.z1;
                 const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M, n0 = n_tile * p.block_n + (int)cta_rank * bn_cta;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                // implicit conv: the tile's pixel-box origin once per tile, (filter row, filter column, channel chunk) of
+                // the k-block as running counters -- no division on the per-k-block path of the issuing thread
+                int cvw0 = 0, cvh0 = 0, cvb0 = 0, cv_r = 0, cv_s = 0, cv_cc = 0;
+                if (p.cv_mode == 1 || p.cv_mode == 2) {
+                    const int wt = m_tile % p.cv_tw, hb_ = m_tile / p.cv_tw;
+                    cvw0 = wt * p.cv_wb; cvh0 = (hb_ % p.cv_th) * p.cv_hb; cvb0 = (hb_ / p.cv_th) * p.cv_bb;
+                    const int tap0 = kb0 / p.cv_cchunks;
+                    cv_cc = kb0 - tap0 * p.cv_cchunks; cv_r = tap0 / p.cv_S; cv_s = tap0 - cv_r * p.cv_S;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * p.stage_bytes;
@@ -347,12 +372,11 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     } else
                     if (p.cv_mode == 1 || p.cv_mode == 2) {
                         // tile = box of output pixels; k-block = (filter tap, 64-channel chunk) of the gathered tensor
-                        const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
-                        const int tap = kb / p.cv_cchunks, cc = kb - tap * p.cv_cchunks;
-                        const int r = tap / p.cv_S, sx = tap - r * p.cv_S;
+                        const int r = cv_r, sx = cv_s, cc = cv_cc, tap = r * p.cv_S + sx;
+                        if (++cv_cc == p.cv_cchunks) { cv_cc = 0; if (++cv_s == p.cv_S) { cv_s = 0; ++cv_r; } }
                         const int dw = p.cv_mode == 1 ? sx - p.cv_pad : p.cv_pad - sx;
                         const int dh = p.cv_mode == 1 ? r - p.cv_pad : p.cv_pad - r;
-                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, wt * p.cv_wb + dw, ht * p.cv_hb + dh, bt * p.cv_bb);
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, cvw0 + dw, cvh0 + dh, cvb0);
                         if (p.cv_mode == 1) {
                             tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, 0, 0);
                         } else {                         // weights [Cout, (tap, cin)] read as an MN-major operand
@@ -399,9 +423,8 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (long long w = work0; w < p.total_work; w += work_step, ++it) {
-                long long t = w / ((long long)p.n_tiles * p.m_tiles);
-                const int ks = (int)(t % p.split_k);
+            for (uint32_t w = work0; w < (uint32_t)p.total_work; w += work_step, ++it) {
+                const int ks = decode_work(w, p).ks;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
                 const int acc = it & 1;
@@ -450,6 +473,8 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // column tile changes (the host sizes the grid so that it rarely does) -- shared float atomics are CAS loops
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int cs_tile = -1;
+        int bufsel = 0;            // staging set in use (epi_bufs == 2): alternates per slab ACROSS tiles, so that "at most
+                                   // one bulk store still reading" always refers to the other set
         float* const cs_acc = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 8 * p.epi_bufs * (f_aux ? 2 : 1) * STG_BYTES);
         auto cs_flush = [&]() {
             if (cs_tile < 0) return;
@@ -471,30 +496,31 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int i = 0; i < 8; ++i) cs[i] = 0.f;
         };
         int it = 0;
-        for (long long w = work0; w < p.total_work; w += work_step, ++it) {
-            long long t = w;
-            const int n_tile = (int)(t % p.n_tiles); t /= p.n_tiles;
-            const int m_tile = (int)(t % p.m_tiles) * CG + (int)cta_rank; t /= p.m_tiles;     // this CTA's 128-row tile
+        for (uint32_t w = work0; w < (uint32_t)p.total_work; w += work_step, ++it) {
+            const WorkItem wi = decode_work(w, p);
+            const int n_tile = wi.n_tile, z0 = wi.z0, z1 = wi.z1;
+            const int m_tile = wi.m_tile * CG + (int)cta_rank;                                // this CTA's 128-row tile
             if (CS && p.colstats && n_tile != cs_tile) { cs_flush(); cs_tile = n_tile; }
-            t /= p.split_k;
-            const int z0 = (int)(t % p.nb0);
-            const int z1 = (int)(t / p.nb0);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             const int m = m_tile * BLOCK_M + quarter * 32 + lane;
             const bool row_ok = m < p.M;
+            int cv_w0 = 0, cv_h0 = 0, cv_b0 = 0;      // implicit conv: origin of this tile's pixel box in the output image
+            if (p.cv_mode == 1 || p.cv_mode == 2) {
+                const int wt = m_tile % p.cv_tw, hb_ = m_tile / p.cv_tw;
+                cv_w0 = wt * p.cv_wb; cv_h0 = (hb_ % p.cv_th) * p.cv_hb; cv_b0 = (hb_ / p.cv_th) * p.cv_bb;
+            }
             uint32_t cs_rows = 0;            // which of this warp's 32 tile rows are samples of the column statistics
             if (CS && p.colstats) {
                 bool row_in = row_ok;
                 if (p.cv_mode) {
                     // a tile row outside the image still holds a value (its taps reach inside): not a sample
                     const int idx = quarter * 32 + lane;
-                    const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
-                    row_in = wt * p.cv_wb + idx % p.cv_wb < p.cv_ow &&
-                             ht * p.cv_hb + (idx / p.cv_wb) % p.cv_hb < p.cv_oh &&
-                             bt * p.cv_bb + idx / (p.cv_wb * p.cv_hb) < p.cv_nb;
+                    row_in = cv_w0 + (idx & (p.cv_wb - 1)) < p.cv_ow &&
+                             cv_h0 + ((idx >> p.cv_lw) & (p.cv_hb - 1)) < p.cv_oh &&
+                             cv_b0 + (idx >> (p.cv_lw + p.cv_lh)) < p.cv_nb;
                 }
                 cs_rows = __ballot_sync(0xffffffffu, row_in);
             }
@@ -508,7 +534,6 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const int set_bytes = (f_aux ? 2 : 1) * STG_BYTES;          // one staging set: out slab (+ aux slab)
                 uint8_t* const stg_base = smem + p.stages * p.stage_bytes + ew * p.epi_bufs * set_bytes;
                 const uint32_t sa_base = smem_u32(stg_base) + lane * 128;
-                int bufsel = 0;
                 const int slab_cols = f_fp32 ? 32 : 64;
                 const int n_slabs = p.block_n / slab_cols;
                 const int row0 = m_tile * BLOCK_M + quarter * 32;
@@ -631,7 +656,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll 8
                             for (int r = 0; r < 32; ++r) {
                                 uint32_t w;
-                                asm("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)) : "memory");
                                 const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
                                 s0 += f.x; s1 += f.y;
                                 q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
@@ -641,7 +666,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             for (int r = 0; r < 32; ++r) {
                                 if ((cs_rows >> r) & 1u) {           // warp-uniform
                                     uint32_t w;
-                                    asm("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)) : "memory");
                                     const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
                                     s0 += f.x; s1 += f.y;
                                     q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
@@ -656,10 +681,9 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (lane == 0) {
                         if (p.cv_mode == 1 || p.cv_mode == 2) {
                             // this warp's 32 tile rows are the pixel box (cv_wb, cv_sh, cv_sb) of the output image
-                            const int wt = m_tile % p.cv_tw, ht = (m_tile / p.cv_tw) % p.cv_th, bt = m_tile / (p.cv_tw * p.cv_th);
                             const int idx0 = quarter * 32;
-                            tma_store_4d(&map_d, stg_out, ncol0, wt * p.cv_wb, ht * p.cv_hb + (idx0 / p.cv_wb) % p.cv_hb,
-                                         bt * p.cv_bb + idx0 / (p.cv_wb * p.cv_hb));
+                            tma_store_4d(&map_d, stg_out, ncol0, cv_w0, cv_h0 + ((idx0 >> p.cv_lw) & (p.cv_hb - 1)),
+                                         cv_b0 + (idx0 >> (p.cv_lw + p.cv_lh)));
                         } else {
                             if (f_aux) tma_store_4d(&map_x, stg_out + STG_BYTES, ncol0, row0, z0, z1);
                             if (p.atomic) tma_reduce_add_4d(&map_d, stg_out, ncol0, row0, z0, z1);
@@ -1000,6 +1024,17 @@ int pick_split_k(long long out_tiles, int num_kb, int ctas) {
     return best;
 }
 
+// Operand ring: a stage holds the A tile plus this CTA's share of the B tile (block_n / cg rows), and the ring is as deep
+// as the shared memory left by the epilogue staging and the column-statistics accumulators allows (narrow column tiles
+// get up to 8 stages: their loads are latency-bound, not capacity-bound).
+void plan_ring(GemmParams& p, bool aux, long long colacc_floats) {
+    p.stage_bytes = A_TILE_BYTES + (p.block_n / p.cg) * BLOCK_K * 2;
+    const long long staging = 8ll * p.epi_bufs * (aux ? 2 : 1) * STG_BYTES;
+    const long long avail = SMEM_BYTES - 1024 - staging - colacc_floats * 4;
+    static const int cap = []() { const char* e = getenv("DFU_GEMM_MAX_STAGES"); return e ? atoi(e) : MAX_STAGES; }();
+    p.stages = (int)min((long long)min(cap, MAX_STAGES), avail / p.stage_bytes);
+}
+
 bool g_attr_set = false;
 // CTA-pair (cta_group::2) kernel for the large GEMMs; DFU_GEMM_PAIR=0 keeps every launch on the single-CTA kernel
 const bool g_pair_enabled = []() { const char* e = getenv("DFU_GEMM_PAIR"); return !(e && e[0] == '0'); }();
@@ -1178,12 +1213,9 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
             if (a->accumulate || w2 * 88 < w1 * 100) p.cg = 2;
         }
     }
-    if (p.cg == 2) {
-        // per CTA and stage: 128 x 64 of A + 128 x 64 of B = 32 KB -> 6 stages (5 next to the 64 KB aux staging)
-        p.stage_bytes = A_TILE_BYTES + (p.block_n / 2) * BLOCK_K * 2;
-        p.stages = (a->aux || a->colstats) ? 5 : 6;       // 5 x 32 KB next to 64 KB of aux staging / 32 KB + accumulators
-        p.epi_bufs = 1;
-    }
+    if (p.cg == 2) p.epi_bufs = 1;
+    // block_n = 256: 4 x 48 KB stages (3 next to aux / colstats staging); a CTA pair: 6 x 32 KB (5); narrower tiles deeper
+    plan_ring(p, a->aux != nullptr, a->colstats ? (long long)a->N * a->colstats_mode : 0);
     p.m_tiles = dfu_cdiv(a->M, BLOCK_M * p.cg);
     p.n_tiles = dfu_cdiv(a->N, p.block_n);
     p.num_kb = dfu_cdiv(a->K, BLOCK_K);
@@ -1195,6 +1227,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     p.kb_per_split = dfu_cdiv(p.num_kb, split);
     p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
     p.total_work = out_tiles * p.split_k;
+    DFU_CHECK_ARG(p.total_work < (1ll << 31) - 4096, "dfu_gemm: %lld work items (32-bit tile index)", p.total_work);
     p.D = a->D; p.ldd = a->ldd; p.sd0 = a->sd0; p.sd1 = a->sd1;
     p.d_fp32 = a->d_dtype; p.atomic = a->accumulate ? (p.split_k > 1 ? 2 : 1) : 0;
     p.aux = (bf16*)a->aux; p.bias = a->bias; p.res = (const bf16*)a->res;
@@ -1281,7 +1314,6 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         DFU_CHECK_ARG(a->mode == 1 && a->Cout <= 2048, "dfu_conv_gemm: colstats is a forward-mode feature (Cout <= 2048)");
         p.colstats = a->colstats;
         p.colstats_mode = 2;
-        p.stages = 3;                    // the per-column accumulators take the fourth stage's shared memory
     }
     p.cv_S = a->S;
     p.cv_pad = a->pad;
@@ -1301,6 +1333,8 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         const bool fwd = a->mode == 1;
         const int OW = fwd ? Wo : a->W, OH = fwd ? Ho : a->H;            // image the output pixels live in
         pick_pixel_box(OW, OH, a->B, BLOCK_M, &p.cv_wb, &p.cv_hb, &p.cv_bb);
+        for (p.cv_lw = 0; (1 << p.cv_lw) < p.cv_wb; ++p.cv_lw) {}
+        for (p.cv_lh = 0; (1 << p.cv_lh) < p.cv_hb; ++p.cv_lh) {}
         p.cv_tw = dfu_cdiv(OW, p.cv_wb);
         p.cv_th = dfu_cdiv(OH, p.cv_hb);
         p.cv_ow = OW; p.cv_oh = OH; p.cv_nb = a->B;
@@ -1314,6 +1348,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.a_mn = 0;
         p.b_mn = fwd ? 0 : 1;
         p.block_n = pick_block_n(p.N, true);
+        plan_ring(p, false, p.colstats ? 2ll * p.N : 0);
         p.n_tiles = dfu_cdiv(p.N, p.block_n);
         p.split_k = 1;
         p.kb_per_split = p.num_kb;
@@ -1333,6 +1368,8 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.d_fp32 = 0;
     } else {
         pick_pixel_box(Wo, Ho, a->B, BLOCK_K, &p.cv_wb, &p.cv_hb, &p.cv_bb);
+        for (p.cv_lw = 0; (1 << p.cv_lw) < p.cv_wb; ++p.cv_lw) {}
+        for (p.cv_lh = 0; (1 << p.cv_lh) < p.cv_hb; ++p.cv_lh) {}
         p.cv_tw = dfu_cdiv(Wo, p.cv_wb);
         p.cv_th = dfu_cdiv(Ho, p.cv_hb);
         p.num_kb = p.cv_tw * p.cv_th * dfu_cdiv(a->B, p.cv_bb);
@@ -1341,6 +1378,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.K = p.num_kb * BLOCK_K;
         p.a_mn = p.b_mn = 1;
         p.block_n = pick_block_n(p.N, true);
+        plan_ring(p, false, p.colstats ? 2ll * p.N : 0);
         p.m_tiles = dfu_cdiv(p.M, BLOCK_M);
         p.n_tiles = dfu_cdiv(p.N, p.block_n);
         const long long out_tiles = (long long)p.m_tiles * p.n_tiles;

@@ -133,7 +133,8 @@ def test_gemm_stored_gelu_derivative_pair(ops, dev, M, N, K, impl):
             close(st, dh.float().sum(0), 1e-4, 2e-3 * (M ** 0.5))
 
 
-@pytest.mark.parametrize("M,N,K,mode,bias", [(5000, 256, 64, 2, 0), (777, 2048, 512, 2, 0), (1000, 3072, 768, 1, 0),
+@pytest.mark.parametrize("M,N,K,mode,bias", [(5000, 256, 64, 2, 0), (50176, 64, 152, 2, 0), (100352, 64, 64, 2, 0),
+                                             (100352, 128, 128, 2, 0), (777, 2048, 512, 2, 0), (1000, 3072, 768, 1, 0),
                                              (300, 64, 147 + 5, 2, 0), (130, 200, 96, 1, 1)])
 def test_gemm_column_statistics_epilogue(ops, dev, M, N, K, mode, bias):
     """colstats: per-column sum (and sum of squares) of the stored results, accumulated by the epilogue."""
