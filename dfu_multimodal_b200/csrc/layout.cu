@@ -264,6 +264,76 @@ __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__
         *reinterpret_cast<bf16x8*>(out + (long long)t * 8) = *reinterpret_cast<const bf16x8*>(e);
     }
 }
+// The same with the filter geometry fixed at compile time (the ResNet stem: 7x7, stride 2, pad 3, ldc 152): one thread
+// assembles a whole col row, so every source offset (filter row r, column j of the S*3 contiguous input elements) is
+// an immediate -- no division, no per-element bounds test for pixels whose window lies inside the image row.
+// (Measured on B200, B=128: 449 us generic -> 270 us; assembling whole output rows in shared memory and draining them
+// with cp.async.bulk was slower, 590 us.)
+template <int R, int S, int STRIDE, int PAD, int LDC>
+__global__ void __launch_bounds__(256) im2col_c3_fixed_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W,
+                                                              int Ho, int Wo) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [(C3_ROWS_PER_BLOCK-1)*STRIDE + R][W*3]
+    const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
+    const int ho0 = (blockIdx.x % hblocks) * C3_ROWS_PER_BLOCK;
+    const int b = blockIdx.x / hblocks;
+    const int nho = min(C3_ROWS_PER_BLOCK, Ho - ho0);
+    const int nrows = (nho - 1) * STRIDE + R;
+    const int rowlen = W * 3;
+    const int vec_per_row = rowlen >> 3;
+    const int h_first = ho0 * STRIDE - PAD;
+    for (int t = threadIdx.x; t < nrows * vec_per_row; t += blockDim.x) {
+        const int r = t / vec_per_row, v = t - r * vec_per_row;
+        const int h = h_first + r;
+        bf16x8 val;
+        if (h >= 0 && h < H) {
+            val = ld8(x + ((long long)b * H + h) * rowlen + v * 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) val.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+        }
+        *reinterpret_cast<bf16x8*>(rows + r * rowlen + v * 8) = val;
+    }
+    __syncthreads();
+    constexpr int SEG = S * 3, KC = R * S * 3, CHUNKS = LDC / 8;
+    const unsigned short* rows16 = reinterpret_cast<const unsigned short*>(rows);
+    bf16* out = col + ((long long)b * Ho + ho0) * Wo * LDC;
+    for (int t = threadIdx.x; t < nho * Wo; t += blockDim.x) {
+        const int hl = t / Wo, wo = t - hl * Wo;
+        const int w0 = (wo * STRIDE - PAD) * 3;
+        const unsigned short* base = rows16 + hl * STRIDE * rowlen + w0;
+        uint4* orow = reinterpret_cast<uint4*>(out + (long long)t * LDC);
+        if (w0 >= 0 && w0 + SEG <= rowlen) {                 // window inside the image row: no per-element tests
+#pragma unroll
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                uint32_t wd[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k0 = ch * 8 + 2 * i, k1 = k0 + 1;
+                    uint32_t lo = 0, hi = 0;
+                    if (k0 < KC) lo = base[(k0 / SEG) * rowlen + (k0 % SEG)];
+                    if (k1 < KC) hi = base[(k1 / SEG) * rowlen + (k1 % SEG)];
+                    wd[i] = lo | (hi << 16);
+                }
+                orow[ch] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                uint32_t wd[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k0 = ch * 8 + 2 * i, k1 = k0 + 1;
+                    uint32_t lo = 0, hi = 0;
+                    if (k0 < KC && w0 + (k0 % SEG) >= 0 && w0 + (k0 % SEG) < rowlen) lo = base[(k0 / SEG) * rowlen + (k0 % SEG)];
+                    if (k1 < KC && w0 + (k1 % SEG) >= 0 && w0 + (k1 % SEG) < rowlen) hi = base[(k1 / SEG) * rowlen + (k1 % SEG)];
+                    wd[i] = lo | (hi << 16);
+                }
+                orow[ch] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
+        }
+    }
+}
 // Zero the pad columns [Kc, ldc) of the vector path when ldc > Kc.
 __global__ void __launch_bounds__(256) zero_pad_cols_kernel(bf16* __restrict__ col, long long rows, int Kc, long long ldc) {
     const int padw = (int)(ldc - Kc);
@@ -420,6 +490,12 @@ extern "C" int dfu_im2col_nhwc(const void* x, void* col, int32_t B, int32_t H, i
     } else if (C == 3 && (W * 3) % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0 &&
                (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16) <= 48 * 1024) {
         const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
+        if (R == 7 && S == 7 && stride == 2 && pad == 3 && ldc == 152) {
+            im2col_c3_fixed_kernel<7, 7, 2, 3, 152><<<B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * 2 + 7) * W * 3 * sizeof(bf16), st>>>(
+                (const bf16*)x, (bf16*)col, H, W, Ho, Wo);
+            DFU_CHECK_LAUNCH("im2col_c3_fixed");
+            return DFU_OK;
+        }
         im2col_c3_kernel<<<B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16), st>>>(
             (const bf16*)x, (bf16*)col, H, W, R, S, stride, pad, Ho, Wo, (int)ldc);
         DFU_CHECK_LAUNCH("im2col_c3");

@@ -302,58 +302,79 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
 // One warp per row, D <= 1024, D % 8 == 0: row kept in registers (<= 4 vectors of 8 per lane).
 constexpr int LN_MAXV = 4;
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, bf16* __restrict__ y,
-                                                        float* __restrict__ stats, long long rows, int D, float eps) {
-    extern __shared__ float sgb[];          // gamma[D], beta[D]: read once per block instead of once per row from L2
-    float* sg = sgb;
-    float* sb = sgb + D;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) { sg[i] = gamma[i]; sb[i] = beta[i]; }
-    __syncthreads();
+template <int NV>
+__global__ void __launch_bounds__(256, 3) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ y,
+                                                           float* __restrict__ stats, long long rows, int D, float eps) {
+    // one warp per row, persistent: the next row's 128-bit loads are in flight while the current row is reduced and
+    // written; the row stays packed (4 registers per vector) and is unpacked in each pass; gamma / beta come through
+    // the read-only path (L1 hits after the first row)
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int nvec = D >> 3;
-    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * warps_per_block) {
-        float v[LN_MAXV][8];
+    const long long stride = (long long)gridDim.x * warps_per_block;
+    long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    bf16x8 raw[NV], nxt[NV];
+    if (row < rows) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nvec) raw[k] = ld8(x + row * D + vi * 8);
+        }
+    }
+    for (; row < rows; row += stride) {
+        const long long nrow = row + stride;
+        if (nrow < rows) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const int vi = lane + k * 32;
+                if (vi < nvec) nxt[k] = ld8(x + nrow * D + vi * 8);
+            }
+        }
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < NV; ++k) {
             const int vi = lane + k * 32;
             if (vi < nvec) {
-                unpack8(ld8(x + row * D + vi * 8), v[k]);
+                float f[8];
+                unpack8(raw[k], f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s += v[k][i];
+                for (int i = 0; i < 8; ++i) s += f[i];
             }
         }
         const float mean = warp_sum(s) / (float)D;
         float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < NV; ++k) {
             const int vi = lane + k * 32;
             if (vi < nvec) {
+                float f[8];
+                unpack8(raw[k], f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
+                for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; q += d * d; }
             }
         }
         const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
         if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < NV; ++k) {
             const int vi = lane + k * 32;
             if (vi < nvec) {
-                float o[8];
-                const float4 g0 = *reinterpret_cast<const float4*>(sg + vi * 8);
-                const float4 g1 = *reinterpret_cast<const float4*>(sg + vi * 8 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(sb + vi * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(sb + vi * 8 + 4);
+                float o[8], f[8];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                unpack8(raw[k], f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
+                for (int i = 0; i < 8; ++i) o[i] = (f[i] - mean) * rstd * gg[i] + bb[i];
                 st8(y + row * D + vi * 8, pack8(o));
             }
         }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) raw[k] = nxt[k];
     }
 }
 
@@ -527,7 +548,9 @@ bool bn_shape_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= 256 && 256 %
 extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, void* stream) {
     DFU_CHECK_ARG(y && sums && M > 0 && bn_shape_ok(C), "dfu_bn_stats: unsupported shape M=%lld C=%d", (long long)M, C);
     const int rpi = 256 / (C / 8);
-    bn_reduce_kernel<0><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+    // every block ends with 2C global atomics: one resident wave (launch bounds: 2 blocks per SM) keeps them at
+    // 296 x 2C -- with 8 blocks per SM the atomics of the wide, short layers (C >= 512) cost more than their loads
+    bn_reduce_kernel<0><<<grid_cap((M + rpi - 1) / rpi, 2), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0, nullptr);
     DFU_CHECK_LAUNCH("bn_stats");
     return DFU_OK;
@@ -577,7 +600,7 @@ extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const uint8_t* z
     DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z || zmask || (gamma && beta)),
                   "dfu_bn_bwd_reduce: bad args");
     const int rpi = 256 / (C / 8);
-    bn_reduce_kernel<1><<<grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream>>>(
+    bn_reduce_kernel<1><<<grid_cap((M + rpi - 1) / rpi, 2), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu, zmask);
     DFU_CHECK_LAUNCH("bn_bwd_reduce");
     return DFU_OK;
@@ -598,8 +621,14 @@ extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const uint8_t* zm
 extern "C" int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
                              int32_t D, float eps, void* stream) {
     DFU_CHECK_ARG(x && gamma && beta && y && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256, "dfu_layernorm: unsupported D=%d", D);
-    layernorm_kernel<<<grid_cap((rows + 7) / 8, 3), 256, 2 * (size_t)D * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
-                                                                                   stats, rows, D, eps);
+    const int grid = grid_cap((rows + 7) / 8, 3);
+    const int nv = (D / 8 + 31) / 32;
+#define DFU_LN_FWD(NV) layernorm_kernel<NV><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y, stats, rows, D, eps)
+    if (nv == 1) DFU_LN_FWD(1);
+    else if (nv == 2) DFU_LN_FWD(2);
+    else if (nv == 3) DFU_LN_FWD(3);
+    else DFU_LN_FWD(4);
+#undef DFU_LN_FWD
     DFU_CHECK_LAUNCH("layernorm");
     return DFU_OK;
 }

@@ -317,76 +317,97 @@ __global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const bf16* __res
 // ------------------------------------------------------------------ pooling
 __global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                       uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+    // one thread = 8 channels of one output pixel; the nine window loads are issued before any is consumed
     const int cv = C >> 3;
-    GRID_STRIDE(t, (long long)B * Ho * Wo * cv) {
-        const int v = (int)(t % cv);
-        const long long pix = t / cv;
+    const unsigned total = (unsigned)B * Ho * Wo * cv;            // host checks < 2^31
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned v = t % cv, pix = t / cv;
         const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const unsigned row = pix / Wo;
+        const int ho = (int)(row % Ho), b = (int)(row / Ho);
+        bf16x8 val[9];
+        bool ok[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int h = ho * 2 - 1 + r, w = wo * 2 - 1 + s;
+                ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+                if (ok[r * 3 + s]) val[r * 3 + s] = ld8(x + (((long long)b * H + h) * W + w) * C + v * 8);
+            }
         float best[8];
-        uint8_t bi[8];
+        uint32_t bi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 255; }
-        for (int r = 0; r < 3; ++r) {
-            const int h = ho * 2 - 1 + r;
-            if (h < 0 || h >= H) continue;
-            for (int s = 0; s < 3; ++s) {
-                const int w = wo * 2 - 1 + s;
-                if (w < 0 || w >= W) continue;
-                float f[8];
-                unpack8(ld8(x + (((long long)b * H + h) * W + w) * C + v * 8), f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (f[i] > best[i] || bi[i] == 255) { best[i] = f[i]; bi[i] = (uint8_t)(r * 3 + s); }
-            }
+        for (int k = 0; k < 9; ++k) {
+            if (!ok[k]) continue;
+            float f[8];
+            unpack8(val[k], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (f[i] > best[i] || bi[i] == 255) { best[i] = f[i]; bi[i] = (uint32_t)k; }
         }
-        st8(y + pix * C + v * 8, pack8(best));
+        st8(y + (long long)pix * C + v * 8, pack8(best));
         if (idx) {
             uint2 packed;
-            packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((uint32_t)bi[3] << 24);
-            packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((uint32_t)bi[7] << 24);
-            *reinterpret_cast<uint2*>(idx + pix * C + v * 8) = packed;
+            packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+            packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+            *reinterpret_cast<uint2*>(idx + (long long)pix * C + v * 8) = packed;
         }
     }
 }
-// gather form: input pixel (h,w) is tap (r,s) of window (ho,wo) iff h = 2ho-1+r, w = 2wo-1+s.
+// gather form: input pixel (h,w) is tap (r,s) of window (ho,wo) iff h = 2ho-1+r, w = 2wo-1+s -- at most 2 x 2 windows
+// (taps of the parity of h+1 / w+1); their winner bytes and gradients are loaded before any is consumed.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dy,
                                                           bf16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
     const int cv = C >> 3;
-    GRID_STRIDE(t, (long long)B * H * W * cv) {
-        const int v = (int)(t % cv);
-        const long long pix = t / cv;
+    const unsigned total = (unsigned)B * H * W * cv;              // host checks < 2^31
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned v = t % cv, pix = t / cv;
         const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long long)W * H));
+        const unsigned row = pix / W;
+        const int h = (int)(row % H), b = (int)(row / H);
+        // rows: h odd -> taps r = 0 (ho = (h+1)/2) and r = 2 (ho = (h-1)/2); h even -> r = 1 (ho = h/2); same for columns
+        int hos[2], rs[2], wos[2], ss[2];
+        if (h & 1) { hos[0] = (h + 1) >> 1; rs[0] = 0; hos[1] = (h - 1) >> 1; rs[1] = 2; }
+        else       { hos[0] = h >> 1; rs[0] = 1; hos[1] = -1; rs[1] = 0; }
+        if (w & 1) { wos[0] = (w + 1) >> 1; ss[0] = 0; wos[1] = (w - 1) >> 1; ss[1] = 2; }
+        else       { wos[0] = w >> 1; ss[0] = 1; wos[1] = -1; ss[1] = 0; }
+        uint2 win[4];
+        bf16x8 gv[4];
+        bool ok[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int k = a * 2 + c;
+                ok[k] = hos[a] >= 0 && hos[a] < Ho && wos[c] >= 0 && wos[c] < Wo;
+                if (ok[k]) {
+                    const long long off = ((((long long)b * Ho + hos[a]) * Wo + wos[c]) * C) + v * 8;
+                    win[k] = *reinterpret_cast<const uint2*>(idx + off);
+                    gv[k] = ld8(dy + off);
+                }
+            }
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int r = 0; r < 3; ++r) {
-            const int hn = h + 1 - r;
-            if (hn < 0 || (hn & 1)) continue;
-            const int ho = hn >> 1;
-            if (ho >= Ho) continue;
-            for (int s = 0; s < 3; ++s) {
-                const int wn = w + 1 - s;
-                if (wn < 0 || (wn & 1)) continue;
-                const int wo = wn >> 1;
-                if (wo >= Wo) continue;
-                const long long op = ((long long)b * Ho + ho) * Wo + wo;
-                const uint2 packed = *reinterpret_cast<const uint2*>(idx + op * C + v * 8);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int k = a * 2 + c;
+                if (!ok[k]) continue;
                 float g[8];
-                unpack8(ld8(dy + op * C + v * 8), g);
-                const uint8_t tap = (uint8_t)(r * 3 + s);
+                unpack8(gv[k], g);
+                const uint32_t tap = (uint32_t)(rs[a] * 3 + ss[c]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint32_t word = (i < 4) ? packed.x : packed.y;
-                    const uint8_t bi = (word >> ((i & 3) * 8)) & 0xFF;
-                    if (bi == tap) acc[i] += g[i];
+                    const uint32_t word = (i < 4) ? win[k].x : win[k].y;
+                    if (((word >> ((i & 3) * 8)) & 0xFFu) == tap) acc[i] += g[i];
                 }
             }
-        }
-        st8(dx + pix * C + v * 8, pack8(acc));
+        st8(dx + (long long)pix * C + v * 8, pack8(acc));
     }
 }
 
@@ -557,7 +578,7 @@ extern "C" int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dc
 }
 
 extern "C" int dfu_maxpool3x3s2(const void* x, void* y, uint8_t* idx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
-    DFU_CHECK_ARG(x && y && B > 0 && C % 8 == 0, "dfu_maxpool3x3s2: bad args");
+    DFU_CHECK_ARG(x && y && B > 0 && C % 8 == 0 && (long long)B * H * W * (C / 8) < (1ll << 31), "dfu_maxpool3x3s2: bad args");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, idx,
                                                                                                      B, H, W, C, Ho, Wo);
@@ -566,7 +587,8 @@ extern "C" int dfu_maxpool3x3s2(const void* x, void* y, uint8_t* idx, int32_t B,
 }
 extern "C" int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
                                     void* stream) {
-    DFU_CHECK_ARG(idx && dy && dx && B > 0 && C % 8 == 0, "dfu_maxpool3x3s2_bwd: bad args");
+    DFU_CHECK_ARG(idx && dy && dx && B > 0 && C % 8 == 0 && (long long)B * H * W * (C / 8) < (1ll << 31),
+                  "dfu_maxpool3x3s2_bwd: bad args");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     maxpool_bwd_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(idx, (const bf16*)dy,
                                                                                                        (bf16*)dx, B, H, W, C, Ho, Wo);

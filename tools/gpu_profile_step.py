@@ -35,6 +35,13 @@ if os.environ.get("PROFILE", "1") == "1":
             agg[ev.name][0] += t
             agg[ev.name][1] += 1
             total += t
+    if os.environ.get("DUMP"):            # every launch in start order: "start_us duration_us name" (single stream: clean)
+        evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda ev: ev.time_range.start)
+        t0 = evs[0].time_range.start
+        with open(os.environ["DUMP"], "w") as f:
+            for ev in evs:
+                f.write("%10.1f %8.1f %s\n" % (ev.time_range.start - t0, ev.device_time, ev.name[:90]))
     print("total device time %.2f ms over %d kernels" % (total / 1e3, sum(v[1] for v in agg.values())))
     for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
         print("%8.2f ms %5.1f%% n=%4d  %s" % (t / 1e3, 100 * t / total, n, name[:110]))
