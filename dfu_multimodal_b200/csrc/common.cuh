@@ -160,4 +160,77 @@ __device__ __forceinline__ void gelu_both_fast(float x, float& g, float& d) {
     d = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue like one FFMA and do two lanes' worth of work).
+// The GEMM epilogues are bound by the FMA pipe of the 8 epilogue warps, so the GELU polynomial runs two elements per op.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_bcast(float c) { return f2_pack(c, c); }
+
+// gelu_both_fast on two elements at once: (x0, x1) -> gelu in (g0, g1), derivative in (d0, d1).  Same arithmetic as the
+// scalar version, except the normal CDF is formed as 0.5 + copysign(0.5 - r/2, x).
+__device__ __forceinline__ void gelu_both_fast2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const uint64_t x = f2_pack(x0, x1), ax = f2_pack(a0, a1);
+    const uint64_t z = f2_mul(ax, f2_bcast(0.70710678118654752440f));
+    uint64_t q = f2_fma(f2_bcast(0.0000430638f), z, f2_bcast(0.0002765672f));
+    q = f2_fma(q, z, f2_bcast(0.0001520143f));
+    q = f2_fma(q, z, f2_bcast(0.0092705272f));
+    q = f2_fma(q, z, f2_bcast(0.0422820123f));
+    q = f2_fma(q, z, f2_bcast(0.0705230784f));
+    q = f2_fma(q, z, f2_bcast(1.0f));
+    q = f2_mul(q, q); q = f2_mul(q, q); q = f2_mul(q, q); q = f2_mul(q, q);
+    float q0, q1, r0, r1, e0, e1, t0, t1;
+    f2_unpack(q, q0, q1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
+    f2_unpack(f2_mul(f2_mul(x, x), f2_bcast(-0.72134752044448170368f)), t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    const uint64_t r = f2_pack(r0, r1), e = f2_pack(e0, e1);
+    // gelu = max(x, 0) - 0.5 |x| r
+    f2_unpack(f2_fma(f2_mul(ax, f2_bcast(-0.5f)), r, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), g0, g1);
+    // Phi = 0.5 + copysign(0.5 - 0.5 r, x);  gelu' = Phi + x phi(x)
+    float h0, h1;
+    f2_unpack(f2_fma(r, f2_bcast(-0.5f), f2_bcast(0.5f)), h0, h1);
+    const uint64_t cdf = f2_add(f2_bcast(0.5f), f2_pack(copysignf(h0, x0), copysignf(h1, x1)));
+    f2_unpack(f2_fma(f2_mul(x, f2_bcast(0.39894228040143267794f)), e, cdf), d0, d1);
+}
+// gelu_fast on two elements at once.
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const uint64_t ax = f2_pack(a0, a1);
+    const uint64_t z = f2_mul(ax, f2_bcast(0.70710678118654752440f));
+    uint64_t q = f2_fma(f2_bcast(0.0000430638f), z, f2_bcast(0.0002765672f));
+    q = f2_fma(q, z, f2_bcast(0.0001520143f));
+    q = f2_fma(q, z, f2_bcast(0.0092705272f));
+    q = f2_fma(q, z, f2_bcast(0.0422820123f));
+    q = f2_fma(q, z, f2_bcast(0.0705230784f));
+    q = f2_fma(q, z, f2_bcast(1.0f));
+    q = f2_mul(q, q); q = f2_mul(q, q); q = f2_mul(q, q); q = f2_mul(q, q);
+    float q0, q1, r0, r1;
+    f2_unpack(q, q0, q1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
+    f2_unpack(f2_fma(f2_mul(ax, f2_bcast(-0.5f)), f2_pack(r0, r1), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), g0, g1);
+}
+
 #endif  // __CUDACC__

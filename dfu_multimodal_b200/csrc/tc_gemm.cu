@@ -599,7 +599,8 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             if (f_act == 4) {                // aux = gelu'(pre-activation), v = gelu(pre-activation)
                                 float dv[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) gelu_both_fast(v[q * 8 + j], v[q * 8 + j], dv[j]);
+                                for (int j = 0; j < 8; j += 2)
+                                    gelu_both_fast2(v[q * 8 + j], v[q * 8 + j + 1], v[q * 8 + j], v[q * 8 + j + 1], dv[j], dv[j + 1]);
                                 pk = pack8(dv);
                             } else {
                                 pk = pack8(v + q * 8);
@@ -612,7 +613,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     } else if (f_act == 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                        for (int j = 0; j < 32; j += 2) gelu_fast2(v[j], v[j + 1], v[j], v[j + 1]);
                     }
                     if (use_res) {
 #pragma unroll
@@ -653,14 +654,17 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         const uint32_t sbase = smem_u32(stg_out) + (lane & 3) * 4;
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                         if (cs_rows == 0xffffffffu) {
+                            uint64_t s2 = f2_pack(0.f, 0.f), q2 = s2;       // both columns per FADD2 / FFMA2
 #pragma unroll 8
                             for (int r = 0; r < 32; ++r) {
                                 uint32_t w;
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)) : "memory");
-                                const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
-                                s0 += f.x; s1 += f.y;
-                                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                                const uint64_t f = f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+                                s2 = f2_add(s2, f);
+                                q2 = f2_fma(f, f, q2);
                             }
+                            f2_unpack(s2, s0, s1);
+                            f2_unpack(q2, q0, q1);
                         } else {
 #pragma unroll 8
                             for (int r = 0; r < 32; ++r) {
