@@ -113,10 +113,33 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: file descriptor 1 is pointed at stderr for the rest of the process, so banners
+    that libraries write to stdout (NCCL's version line under NCCL_DEBUG=VERSION, for one) cannot precede it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -322,7 +345,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "tflops_per_gpu": value / n_gpus * TRAIN_GFLOP_PER_PAIR / 1e3,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         # The captured CUDA graphs hold NCCL work on the communicator: tearing the process group down while they are alive
         # blocks (measured: destroy_process_group never returns).  All ranks are done and in step here, so leave directly.
