@@ -66,6 +66,7 @@ struct GemmParams {
     int cv_wb, cv_hb, cv_bb;  // pixel box of one tile (128 output pixels, or 64 pixels per k-block for wgrad)
     int cv_tw, cv_th;         // boxes per image row / column
     int cv_lw, cv_lh;         // log2(cv_wb), log2(cv_hb): the box sides are powers of two
+    int cv_stride;            // convolution stride (forward / wgrad): the gathered box walks the input with this step
     int cv_S, cv_pad;         // filter width, padding
     int cv_cchunks;           // 64-channel chunks of the gathered tensor (fwd: Cin/64, dgrad: Cout/64)
     int cv_C;                 // channels of the tap-major weight columns (Cin)
@@ -376,7 +377,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         if (++cv_cc == p.cv_cchunks) { cv_cc = 0; if (++cv_s == p.cv_S) { cv_s = 0; ++cv_r; } }
                         const int dw = p.cv_mode == 1 ? sx - p.cv_pad : p.cv_pad - sx;
                         const int dh = p.cv_mode == 1 ? r - p.cv_pad : p.cv_pad - r;
-                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, cvw0 + dw, cvh0 + dh, cvb0);
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, cvw0 * p.cv_stride + dw, cvh0 * p.cv_stride + dh, cvb0);
                         if (p.cv_mode == 1) {
                             tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, 0, 0);
                         } else {                         // weights [Cout, (tap, cin)] read as an MN-major operand
@@ -394,7 +395,8 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             const int ncol = n0 + j * 64;
                             const int tap = ncol / p.cv_C, c0 = ncol - tap * p.cv_C;
                             const int r = tap / p.cv_S, sx = tap - r * p.cv_S;
-                            tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, c0, w0 + sx - p.cv_pad, h0 + r - p.cv_pad, b0);
+                            tma_load_4d(&map_b, &full_bar[stage], sb + j * 8192, c0, w0 * p.cv_stride + sx - p.cv_pad,
+                                        h0 * p.cv_stride + r - p.cv_pad, b0);
                         }
                     } else if (!p.a_mn) {
                         tma_load_4d(&map_a, &full_bar[stage], sa, k0, m0, z0, z1);
@@ -967,11 +969,13 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long rows
 
 // General 4-D bf16/fp32 map: dims/strides in elements (stride[0] is implicit 1), box and traversal strides per dim.
 int make_map_nd(CUtensorMap* map, const void* base, const long long dims_[4], const long long strides_[3], const int box_[4],
-                int esz = 2) {
+                int esz = 2, int walk = 1) {
+    // walk > 1: the box steps through dims 1 and 2 (image width / height) with that stride; box_ then counts tensor
+    // elements spanned, ceil(box / walk) of them land in shared memory (a strided convolution's gathered pixels)
     auto enc = get_encode();
     if (!enc) { dfu_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DFU_ERR_CUDA; }
     cuuint64_t dims[4], strides[3];
-    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4], estr[4] = {1, (cuuint32_t)walk, (cuuint32_t)walk, 1};
     for (int i = 0; i < 4; ++i) { dims[i] = (cuuint64_t)dims_[i]; box[i] = (cuuint32_t)box_[i]; }
     for (int i = 0; i < 3; ++i) strides[i] = (cuuint64_t)strides_[i] * esz;
     CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
@@ -1290,12 +1294,12 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     DFU_CHECK_ARG(a != nullptr, "dfu_conv_gemm: null args");
     DFU_CHECK_ARG(a->mode >= 1 && a->mode <= 3, "dfu_conv_gemm: mode %d", a->mode);
     DFU_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->R > 0 && a->S > 0 && a->pad >= 0, "dfu_conv_gemm: bad geometry");
-    if (a->stride != 1 || a->C % 64 != 0 || a->Cout % 64 != 0) {
-        dfu_set_error("dfu_conv_gemm: needs stride 1 and channel counts that are multiples of 64 (C=%d, Cout=%d, stride=%d)",
-                      a->C, a->Cout, a->stride);
+    if ((a->stride != 1 && !(a->stride == 2 && a->mode != 2)) || a->C % 64 != 0 || a->Cout % 64 != 0) {
+        dfu_set_error("dfu_conv_gemm: needs stride 1 (or 2 for forward / wgrad) and channel counts that are multiples of 64 "
+                      "(C=%d, Cout=%d, stride=%d, mode=%d)", a->C, a->Cout, a->stride, a->mode);
         return DFU_ERR_UNSUPPORTED;
     }
-    const int Ho = a->H + 2 * a->pad - a->R + 1, Wo = a->W + 2 * a->pad - a->S + 1;
+    const int Ho = (a->H + 2 * a->pad - a->R) / a->stride + 1, Wo = (a->W + 2 * a->pad - a->S) / a->stride + 1;
     DFU_CHECK_ARG(Ho > 0 && Wo > 0, "dfu_conv_gemm: empty output");
     DFU_CHECK_ARG(a->out && (a->mode == 2 || a->x) && (a->mode == 3 || a->w) && (a->mode == 1 || a->dy),
                   "dfu_conv_gemm: null operand for mode %d", a->mode);
@@ -1322,6 +1326,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     p.cv_S = a->S;
     p.cv_pad = a->pad;
     p.cv_C = a->C;
+    p.cv_stride = a->stride;
     const int taps = a->R * a->S;
     const int num_sms = dfu_num_sms();
     const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
@@ -1359,9 +1364,9 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         const int rem = 32 / p.cv_wb;
         p.cv_sh = p.cv_hb < rem ? p.cv_hb : rem;
         p.cv_sb = rem / p.cv_sh;
-        const int abox[4] = {64, p.cv_wb, p.cv_hb, p.cv_bb};
+        const int abox[4] = {64, p.cv_wb * a->stride, p.cv_hb * a->stride, p.cv_bb};      // stride > 1: forward only
         const int dbox[4] = {64, p.cv_wb, p.cv_sh, p.cv_sb};
-        rc = make_map_nd(&map_a, fwd ? a->x : a->dy, fwd ? xd : yd, fwd ? xs : ys, abox);
+        rc = make_map_nd(&map_a, fwd ? a->x : a->dy, fwd ? xd : yd, fwd ? xs : ys, abox, 2, a->stride);
         if (rc) return rc;
         if (fwd) rc = make_map(&map_b, a->w, p.K, p.N, a->ldw, 1, 0, 1, 0, BLOCK_K, p.block_n);
         else     rc = make_map(&map_b, a->w, (long long)taps * a->C, a->Cout, a->ldw, 1, 0, 1, 0, 64, BLOCK_K);
@@ -1392,9 +1397,10 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.split_k = dfu_cdiv(p.num_kb, p.kb_per_split);
         p.atomic = a->accumulate ? (p.split_k > 1 ? 2 : 1) : 0;
         const int box[4] = {64, p.cv_wb, p.cv_hb, p.cv_bb};
+        const int xbox[4] = {64, p.cv_wb * a->stride, p.cv_hb * a->stride, p.cv_bb};
         rc = make_map_nd(&map_a, a->dy, yd, ys, box);
         if (rc) return rc;
-        rc = make_map_nd(&map_b, a->x, xd, xs, box);
+        rc = make_map_nd(&map_b, a->x, xd, xs, xbox, 2, a->stride);
         if (rc) return rc;
         rc = make_map(&map_d, a->out, p.N, p.M, a->ldo, 1, 0, 1, 0, 32, 32, 4);
         if (rc) return rc;

@@ -142,7 +142,7 @@ class Conv2dFn(Function):
         if implicit:
             # tiles gathered by TMA straight from the activation tensor: no im2col matrix, x itself is what is saved
             sums = ops.zeros(2 * Cout, F32, xn.device) if (want_stats and FUSE_BN_STATS and Cout <= 2048) else None
-            y = ops.conv_forward(xn, wm, R, S, pad, colstats=sums).view(B * Ho * Wo, Cout)
+            y = ops.conv_forward(xn, wm, R, S, pad, colstats=sums, stride=stride).view(B * Ho * Wo, Cout)
             if want_stats and sums is None:
                 sums = ops.bn_stats(y)
             ctx.geom = (B, H, W, C, Cout, R, S, stride, pad, Ho, Wo, Kc, ldc, False)
@@ -185,9 +185,13 @@ class Conv2dFn(Function):
             gn = ops.as_nhwc(gy)
             dw = dx = None
             if ctx.needs_input_grad[1]:
-                dw = ops.conv_wgrad(gn, A, R, S, pad).reshape(Cout, R, S, C).permute(0, 3, 1, 2)
+                dw = ops.conv_wgrad(gn, A, R, S, pad, stride).reshape(Cout, R, S, C).permute(0, 3, 1, 2)
             if ctx.needs_input_grad[0]:
-                dx = ops.conv_dgrad(gn, conv_weight_matrix(weight), H, W, C, R, S, pad)
+                if stride == 1:
+                    dx = ops.conv_dgrad(gn, conv_weight_matrix(weight), H, W, C, R, S, pad)
+                else:       # strided dgrad: GEMM to the column matrix, then the scatter-free col2im gather
+                    dcol = ops.linear_dgrad(gn.reshape(B * Ho * Wo, Cout), conv_weight_matrix(weight), ldc)
+                    dx = ops.col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
                 if gskip is not None:
                     dx = ops.add(dx, ops.as_nhwc(gskip))
                 dx = dx.permute(0, 3, 1, 2)

@@ -234,14 +234,16 @@ def set_conv_impl(impl):
 
 
 def conv_implicit_ok(C, Cout, R, S, stride):
-    """Shapes dfu_conv_gemm takes: stride 1, channel counts multiples of 64, a real spatial filter."""
-    return _CONV_IMPL == "implicit" and stride == 1 and R * S > 1 and C % 64 == 0 and Cout % 64 == 0
+    """Shapes dfu_conv_gemm takes: channel counts multiples of 64; stride 1 with a real spatial filter (1x1/s1 is a plain
+    GEMM on the activation matrix) or stride 2 (forward and wgrad gather strided pixel boxes; dgrad stays explicit)."""
+    return _CONV_IMPL == "implicit" and C % 64 == 0 and Cout % 64 == 0 and ((stride == 1 and R * S > 1) or stride == 2)
 
 
-def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False, colstats=None):
+def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False, colstats=None,
+               stride=1):
     a = ConvArgs()
     a.mode, a.B, a.H, a.W, a.C = mode, B, H, W, C
-    a.Cout, a.R, a.S, a.stride, a.pad = Cout, R, S, 1, pad
+    a.Cout, a.R, a.S, a.stride, a.pad = Cout, R, S, stride, pad
     a.x, a.w, a.ldw, a.dy = _p(x), _p(w), (w.stride(0) if w is not None else 0), _p(dy)
     a.out, a.ldo, a.accumulate, a.max_ctas = _p(out), ldo, 1 if accumulate else 0, 0
     a.colstats = _p(colstats)
@@ -258,15 +260,15 @@ def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=N
     return out
 
 
-def conv_forward(x_nhwc, wm, R, S, pad, colstats=None):
-    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1.
+def conv_forward(x_nhwc, wm, R, S, pad, colstats=None, stride=1):
+    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1 or 2.
     colstats ([2*Cout] fp32, zeroed) += per-channel sum / sum of squares of y (BatchNorm batch statistics)."""
     _need_cuda(x_nhwc, wm)
     B, H, W, C = x_nhwc.shape
     Cout = wm.shape[0]
-    Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     y = torch.empty((B, Ho, Wo, Cout), dtype=BF16, device=x_nhwc.device)
-    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats)
+    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats, stride=stride)
 
 
 def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad):
@@ -275,14 +277,14 @@ def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad):
     return _conv_call(2, B, H, W, C, Cout, R, S, pad, w=wm, dy=dy_nhwc, out=dx)
 
 
-def conv_wgrad(dy_nhwc, x_nhwc, R, S, pad):
+def conv_wgrad(dy_nhwc, x_nhwc, R, S, pad, stride=1):
     """dW [Cout, R*S*C] fp32 (columns ordered (r,s,c))."""
     B, H, W, C = x_nhwc.shape
     Cout = dy_nhwc.shape[3]
     N = R * S * C
     split = _wgrad_needs_splitk(Cout, N)
     dw = zeros((Cout, N), F32, x_nhwc.device) if split else torch.empty((Cout, N), dtype=F32, device=x_nhwc.device)
-    return _conv_call(3, B, H, W, C, Cout, R, S, pad, x=x_nhwc, dy=dy_nhwc, out=dw, ldo=N, accumulate=split)
+    return _conv_call(3, B, H, W, C, Cout, R, S, pad, x=x_nhwc, dy=dy_nhwc, out=dw, ldo=N, accumulate=split, stride=stride)
 
 
 # ------------------------------------------------------------------------------------------ layout

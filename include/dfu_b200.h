@@ -69,10 +69,12 @@ typedef struct {
 int dfu_gemm(const dfu_gemm_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Implicit-GEMM convolution on NHWC bf16 (stride 1, channel counts multiples of 64): the same tcgen05 kernel, with the
+ * Implicit-GEMM convolution on NHWC bf16 (channel counts multiples of 64; stride 1, or stride 2 for modes 1 and 3 where
+ * the gathered boxes walk the input with TMA element strides): the same tcgen05 kernel, with the
  * operand tiles gathered by TMA from the activation tensor as boxes of pixels shifted by the filter tap (padding =
  * TMA out-of-bounds zero fill).  No im2col / col2im matrix exists.  Replaces cudnn convolution forward / backward
- * data / backward filter for the 3x3 convolutions of torchvision's Bottleneck (train_multimodal_fusion.py:294).
+ * data / backward filter for the 3x3 and strided 1x1 convolutions of torchvision's Bottleneck
+ * (train_multimodal_fusion.py:294).
  *   mode 1: out = y  [B,Ho,Wo,Cout] bf16  from x [B,H,W,C] and w [Cout, ldw] (columns ordered (r, s, c))
  *   mode 2: out = dx [B,H,W,C]      bf16  from dy [B,Ho,Wo,Cout] and w
  *   mode 3: out = dW [Cout, ldo]    fp32  from dy and x; accumulate=1: dW += (caller zeroes; enables split-K)

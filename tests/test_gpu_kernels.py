@@ -255,17 +255,30 @@ def test_im2col_col2im(ops, dev, C, R, stride, pad, H):
                                                 (2, 9, 9, 128, 64, 5, 2), (2, 12, 12, 64, 64, 3, 0)])
 def test_implicit_gemm_convolution(ops, dev, B, H, W, C, Cout, R, pad):
     """dfu_conv_gemm (TMA-gathered tiles, no im2col matrix) against torch conv2d forward / input grad / weight grad."""
-    assert ops.conv_implicit_ok(C, Cout, R, R, 1)
+    _implicit_conv_case(ops, dev, B, H, W, C, Cout, R, pad, 1)
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,R,pad", [(2, 56, 56, 128, 128, 3, 1), (3, 28, 28, 256, 256, 3, 1), (5, 14, 14, 512, 512, 3, 1),
+                                                (2, 56, 56, 256, 512, 1, 0), (3, 14, 14, 1024, 2048, 1, 0), (1, 11, 13, 64, 128, 3, 1),
+                                                (33, 10, 10, 64, 64, 1, 0)])
+def test_implicit_gemm_convolution_stride2(ops, dev, B, H, W, C, Cout, R, pad):
+    """Stride 2 (the first 3x3 and the 1x1 downsample of layer2-4): forward and weight gradient gather strided pixel
+    boxes (TMA element strides); the input gradient of these layers stays on the explicit GEMM + col2im path."""
+    _implicit_conv_case(ops, dev, B, H, W, C, Cout, R, pad, 2)
+
+
+def _implicit_conv_case(ops, dev, B, H, W, C, Cout, R, pad, stride):
+    assert ops.conv_implicit_ok(C, Cout, R, R, stride)
     x = rnd(dev, B, C, H, W)
     w = rnd(dev, Cout, C, R, R, scale=0.05)
     xn = x.permute(0, 2, 3, 1).contiguous()                              # NHWC bf16
     wm = w.permute(0, 2, 3, 1).reshape(Cout, R * R * C).contiguous()     # columns ordered (r, s, c)
     # float64 CPU reference: cuDNN's fp32 algorithms (TF32, FFT, Winograd) are less exact than fp32 accumulation
     xf, wf = x.double().cpu().requires_grad_(True), w.double().cpu().requires_grad_(True)
-    ref = F.conv2d(xf, wf, padding=pad)
+    ref = F.conv2d(xf, wf, padding=pad, stride=stride)
     Ho, Wo = ref.shape[2], ref.shape[3]
     st = torch.zeros(2 * Cout, dtype=torch.float32, device=dev)
-    y = ops.conv_forward(xn, wm, R, R, pad, colstats=st)
+    y = ops.conv_forward(xn, wm, R, R, pad, colstats=st, stride=stride)
     assert y.shape == (B, Ho, Wo, Cout)
     close(y.permute(0, 3, 1, 2), ref, 2 * BF16_EPS, 2e-3)
     # BatchNorm batch sums from the epilogue == a pass over the stored output (tile rows outside the image excluded)
@@ -275,9 +288,10 @@ def test_implicit_gemm_convolution(ops, dev, B, H, W, C, Cout, R, pad):
     dy = rnd(dev, B, Cout, Ho, Wo)
     ref.backward(dy.double().cpu())
     dyn = dy.permute(0, 2, 3, 1).contiguous()
-    dx = ops.conv_dgrad(dyn, wm, H, W, C, R, R, pad)
-    close(dx.permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 2e-3)
-    dw = ops.conv_wgrad(dyn, xn, R, R, pad)
+    if stride == 1:
+        dx = ops.conv_dgrad(dyn, wm, H, W, C, R, R, pad)
+        close(dx.permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 2e-3)
+    dw = ops.conv_wgrad(dyn, xn, R, R, pad, stride)
     close(dw.view(Cout, R, R, C).permute(0, 3, 1, 2), wf.grad, 1e-4, 1e-2)
 
 
