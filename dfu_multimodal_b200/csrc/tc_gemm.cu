@@ -67,6 +67,10 @@ struct GemmParams {
     int cv_tw, cv_th;         // boxes per image row / column
     int cv_lw, cv_lh;         // log2(cv_wb), log2(cv_hb): the box sides are powers of two
     int cv_stride;            // convolution stride (forward / wgrad): the gathered box walks the input with this step
+    // dgrad (mode 2) taps of this launch: r = cv_r0 + i * cv_tstep (i < cv_nr), s = cv_s0 + j * cv_tstep (j < cv_ns); the
+    // gathered dy pixel of output pixel (h, w) of the launch's output view is (h + (cv_ph + pad - r) / cv_tstep, ...).
+    // Stride 1: one launch, tstep 1, all taps.  Stride 2: one launch per parity class (cv_ph, cv_pw) of the dx pixels.
+    int cv_r0, cv_s0, cv_nr, cv_ns, cv_tstep, cv_ph, cv_pw;
     int cv_S, cv_pad;         // filter width, padding
     int cv_cchunks;           // 64-channel chunks of the gathered tensor (fwd: Cin/64, dgrad: Cout/64)
     int cv_C;                 // channels of the tap-major weight columns (Cin)
@@ -373,10 +377,13 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     } else
                     if (p.cv_mode == 1 || p.cv_mode == 2) {
                         // tile = box of output pixels; k-block = (filter tap, 64-channel chunk) of the gathered tensor
-                        const int r = cv_r, sx = cv_s, cc = cv_cc, tap = r * p.cv_S + sx;
-                        if (++cv_cc == p.cv_cchunks) { cv_cc = 0; if (++cv_s == p.cv_S) { cv_s = 0; ++cv_r; } }
-                        const int dw = p.cv_mode == 1 ? sx - p.cv_pad : p.cv_pad - sx;
-                        const int dh = p.cv_mode == 1 ? r - p.cv_pad : p.cv_pad - r;
+                        const bool fwd = p.cv_mode == 1;
+                        const int r = fwd ? cv_r : p.cv_r0 + cv_r * p.cv_tstep, sx = fwd ? cv_s : p.cv_s0 + cv_s * p.cv_tstep;
+                        const int cc = cv_cc, tap = r * p.cv_S + sx;
+                        if (++cv_cc == p.cv_cchunks) { cv_cc = 0; if (++cv_s == (fwd ? p.cv_S : p.cv_ns)) { cv_s = 0; ++cv_r; } }
+                        // dgrad: exact division (the class's taps have the parity of ph + pad), possibly of a negative number
+                        const int dw = fwd ? sx - p.cv_pad : (p.cv_pw + p.cv_pad - sx) >> (p.cv_tstep - 1);
+                        const int dh = fwd ? r - p.cv_pad : (p.cv_ph + p.cv_pad - r) >> (p.cv_tstep - 1);
                         tma_load_4d(&map_a, &full_bar[stage], sa, cc * 64, cvw0 * p.cv_stride + dw, cvh0 * p.cv_stride + dh, cvb0);
                         if (p.cv_mode == 1) {
                             tma_load_4d(&map_b, &full_bar[stage], sb, k0, n0, 0, 0);
@@ -1289,14 +1296,46 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
 
 
 // ----------------------------------------------------------------------------- implicit-GEMM convolution
+namespace {
+int conv_gemm_launch(const dfu_conv_args* a, cudaStream_t stream, int ph, int pw);
+}
+
 extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DFU_CHECK_ARG(a != nullptr, "dfu_conv_gemm: null args");
+    if (a->mode == 2 && a->stride == 2) {
+        // input gradient of a stride-2 convolution: the dx pixels of one parity class (h % 2, w % 2) see a fixed subset of
+        // the filter taps at unit-stride dy offsets, so each class is an ordinary implicit GEMM whose output view is dx
+        // with doubled pixel strides.  Classes without taps (1x1 filters: every odd row / column) are zero.
+        bool any_empty = false;
+        for (int c = 0; c < 4; ++c) {
+            const int r0 = ((c >> 1) + a->pad) & 1, s0 = ((c & 1) + a->pad) & 1;
+            if (r0 >= a->R || s0 >= a->S) any_empty = true;
+        }
+        if (any_empty) {
+            cudaError_t e = cudaMemsetAsync(a->out, 0, (size_t)a->B * a->H * a->W * a->C * 2, stream);
+            if (e != cudaSuccess) { dfu_set_error("dfu_conv_gemm: memset failed: %s", cudaGetErrorString(e)); return DFU_ERR_CUDA; }
+        }
+        for (int c = 0; c < 4; ++c) {
+            const int ph = c >> 1, pw = c & 1;
+            const int r0 = (ph + a->pad) & 1, s0 = (pw + a->pad) & 1;
+            if (r0 >= a->R || s0 >= a->S || ph >= a->H || pw >= a->W) continue;
+            const int rc = conv_gemm_launch(a, stream, ph, pw);
+            if (rc) return rc;
+        }
+        return DFU_OK;
+    }
+    return conv_gemm_launch(a, stream, 0, 0);
+}
+
+namespace {
+int conv_gemm_launch(const dfu_conv_args* a, cudaStream_t stream, int ph, int pw) {
+    DFU_CHECK_ARG(a != nullptr, "dfu_conv_gemm: null args");
     DFU_CHECK_ARG(a->mode >= 1 && a->mode <= 3, "dfu_conv_gemm: mode %d", a->mode);
     DFU_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->R > 0 && a->S > 0 && a->pad >= 0, "dfu_conv_gemm: bad geometry");
-    if ((a->stride != 1 && !(a->stride == 2 && a->mode != 2)) || a->C % 64 != 0 || a->Cout % 64 != 0) {
-        dfu_set_error("dfu_conv_gemm: needs stride 1 (or 2 for forward / wgrad) and channel counts that are multiples of 64 "
-                      "(C=%d, Cout=%d, stride=%d, mode=%d)", a->C, a->Cout, a->stride, a->mode);
+    if ((a->stride != 1 && a->stride != 2) || a->C % 64 != 0 || a->Cout % 64 != 0) {
+        dfu_set_error("dfu_conv_gemm: needs stride 1 or 2 and channel counts that are multiples of 64 (C=%d, Cout=%d, stride=%d)",
+                      a->C, a->Cout, a->stride);
         return DFU_ERR_UNSUPPORTED;
     }
     const int Ho = (a->H + 2 * a->pad - a->R) / a->stride + 1, Wo = (a->W + 2 * a->pad - a->S) / a->stride + 1;
@@ -1326,7 +1365,7 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     p.cv_S = a->S;
     p.cv_pad = a->pad;
     p.cv_C = a->C;
-    p.cv_stride = a->stride;
+    p.cv_stride = a->mode == 2 ? 1 : a->stride;      // dgrad gathers dy at unit stride (per parity class at stride 2)
     const int taps = a->R * a->S;
     const int num_sms = dfu_num_sms();
     const int max_ctas = a->max_ctas > 0 ? a->max_ctas : num_sms;
@@ -1340,7 +1379,14 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     int rc;
     if (a->mode == 1 || a->mode == 2) {
         const bool fwd = a->mode == 1;
-        const int OW = fwd ? Wo : a->W, OH = fwd ? Ho : a->H;            // image the output pixels live in
+        const int tstep = fwd ? 1 : a->stride;
+        // image the output pixels live in (dgrad at stride 2: the dx pixels of parity class (ph, pw))
+        const int OW = fwd ? Wo : (a->W - pw + tstep - 1) / tstep, OH = fwd ? Ho : (a->H - ph + tstep - 1) / tstep;
+        p.cv_tstep = tstep; p.cv_ph = ph; p.cv_pw = pw;
+        p.cv_r0 = fwd ? 0 : (ph + a->pad) % tstep; p.cv_s0 = fwd ? 0 : (pw + a->pad) % tstep;
+        p.cv_nr = fwd ? a->R : (a->R - p.cv_r0 + tstep - 1) / tstep;
+        p.cv_ns = fwd ? a->S : (a->S - p.cv_s0 + tstep - 1) / tstep;
+        const int ntaps = p.cv_nr * p.cv_ns;
         pick_pixel_box(OW, OH, a->B, BLOCK_M, &p.cv_wb, &p.cv_hb, &p.cv_bb);
         for (p.cv_lw = 0; (1 << p.cv_lw) < p.cv_wb; ++p.cv_lw) {}
         for (p.cv_lh = 0; (1 << p.cv_lh) < p.cv_hb; ++p.cv_lh) {}
@@ -1351,9 +1397,9 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         p.M = p.m_tiles * BLOCK_M;
         p.N = fwd ? a->Cout : a->C;
         const int gathered_c = fwd ? a->C : a->Cout;
-        p.K = taps * gathered_c;
+        p.K = ntaps * gathered_c;
         p.cv_cchunks = gathered_c / 64;
-        p.num_kb = taps * p.cv_cchunks;
+        p.num_kb = ntaps * p.cv_cchunks;
         p.a_mn = 0;
         p.b_mn = fwd ? 0 : 1;
         p.block_n = pick_block_n(p.N, true);
@@ -1364,14 +1410,22 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
         const int rem = 32 / p.cv_wb;
         p.cv_sh = p.cv_hb < rem ? p.cv_hb : rem;
         p.cv_sb = rem / p.cv_sh;
-        const int abox[4] = {64, p.cv_wb * a->stride, p.cv_hb * a->stride, p.cv_bb};      // stride > 1: forward only
+        const int walk = fwd ? a->stride : 1;                     // forward: the gathered box steps through x
+        const int abox[4] = {64, p.cv_wb * walk, p.cv_hb * walk, p.cv_bb};
         const int dbox[4] = {64, p.cv_wb, p.cv_sh, p.cv_sb};
-        rc = make_map_nd(&map_a, fwd ? a->x : a->dy, fwd ? xd : yd, fwd ? xs : ys, abox, 2, a->stride);
+        rc = make_map_nd(&map_a, fwd ? a->x : a->dy, fwd ? xd : yd, fwd ? xs : ys, abox, 2, walk);
         if (rc) return rc;
         if (fwd) rc = make_map(&map_b, a->w, p.K, p.N, a->ldw, 1, 0, 1, 0, BLOCK_K, p.block_n);
         else     rc = make_map(&map_b, a->w, (long long)taps * a->C, a->Cout, a->ldw, 1, 0, 1, 0, 64, BLOCK_K);
         if (rc) return rc;
-        rc = make_map_nd(&map_d, a->out, fwd ? yd : xd, fwd ? ys : xs, dbox);
+        if (fwd || tstep == 1) {
+            rc = make_map_nd(&map_d, a->out, fwd ? yd : xd, fwd ? ys : xs, dbox);
+        } else {
+            // output view = the (ph, pw) sub-grid of dx: pixel strides doubled, origin at pixel (ph, pw)
+            const long long vd[4] = {a->C, OW, OH, a->B};
+            const long long vs[3] = {(long long)tstep * a->C, (long long)tstep * a->W * a->C, (long long)a->H * a->W * a->C};
+            rc = make_map_nd(&map_d, (const bf16*)a->out + ((long long)ph * a->W + pw) * a->C, vd, vs, dbox);
+        }
         if (rc) return rc;
         p.D = a->out;
         p.d_fp32 = 0;
@@ -1424,3 +1478,4 @@ extern "C" int dfu_conv_gemm(const dfu_conv_args* a, void* stream_) {
     DFU_CHECK_LAUNCH("dfu_tc_gemm_kernel(conv)");
     return DFU_OK;
 }
+}  // namespace

@@ -187,11 +187,7 @@ class Conv2dFn(Function):
             if ctx.needs_input_grad[1]:
                 dw = ops.conv_wgrad(gn, A, R, S, pad, stride).reshape(Cout, R, S, C).permute(0, 3, 1, 2)
             if ctx.needs_input_grad[0]:
-                if stride == 1:
-                    dx = ops.conv_dgrad(gn, conv_weight_matrix(weight), H, W, C, R, S, pad)
-                else:       # strided dgrad: GEMM to the column matrix, then the scatter-free col2im gather
-                    dcol = ops.linear_dgrad(gn.reshape(B * Ho * Wo, Cout), conv_weight_matrix(weight), ldc)
-                    dx = ops.col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc)
+                dx = ops.conv_dgrad(gn, conv_weight_matrix(weight), H, W, C, R, S, pad, stride)
                 if gskip is not None:
                     dx = ops.add(dx, ops.as_nhwc(gskip))
                 dx = dx.permute(0, 3, 1, 2)

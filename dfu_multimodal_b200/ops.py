@@ -235,7 +235,7 @@ def set_conv_impl(impl):
 
 def conv_implicit_ok(C, Cout, R, S, stride):
     """Shapes dfu_conv_gemm takes: channel counts multiples of 64; stride 1 with a real spatial filter (1x1/s1 is a plain
-    GEMM on the activation matrix) or stride 2 (forward and wgrad gather strided pixel boxes; dgrad stays explicit)."""
+    GEMM on the activation matrix) or stride 2 (forward and wgrad gather strided pixel boxes; dgrad runs per parity class)."""
     return _CONV_IMPL == "implicit" and C % 64 == 0 and Cout % 64 == 0 and ((stride == 1 and R * S > 1) or stride == 2)
 
 
@@ -271,10 +271,11 @@ def conv_forward(x_nhwc, wm, R, S, pad, colstats=None, stride=1):
     return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats, stride=stride)
 
 
-def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad):
+def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad, stride=1):
+    """dx [B,H,W,C].  Stride 2: one implicit GEMM per parity class of the dx pixels (each sees a fixed subset of the taps)."""
     B, Ho, Wo, Cout = dy_nhwc.shape
     dx = torch.empty((B, H, W, C), dtype=BF16, device=dy_nhwc.device)
-    return _conv_call(2, B, H, W, C, Cout, R, S, pad, w=wm, dy=dy_nhwc, out=dx)
+    return _conv_call(2, B, H, W, C, Cout, R, S, pad, w=wm, dy=dy_nhwc, out=dx, stride=stride)
 
 
 def conv_wgrad(dy_nhwc, x_nhwc, R, S, pad, stride=1):

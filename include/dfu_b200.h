@@ -69,8 +69,9 @@ typedef struct {
 int dfu_gemm(const dfu_gemm_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Implicit-GEMM convolution on NHWC bf16 (channel counts multiples of 64; stride 1, or stride 2 for modes 1 and 3 where
- * the gathered boxes walk the input with TMA element strides): the same tcgen05 kernel, with the
+ * Implicit-GEMM convolution on NHWC bf16 (channel counts multiples of 64; stride 1 or 2 -- at stride 2 the gathered
+ * boxes of modes 1 and 3 walk the input with TMA element strides and mode 2 runs one launch per parity class of the dx
+ * pixels, each writing a strided view of dx): the same tcgen05 kernel, with the
  * operand tiles gathered by TMA from the activation tensor as boxes of pixels shifted by the filter tap (padding =
  * TMA out-of-bounds zero fill).  No im2col / col2im matrix exists.  Replaces cudnn convolution forward / backward
  * data / backward filter for the 3x3 and strided 1x1 convolutions of torchvision's Bottleneck

@@ -263,7 +263,7 @@ def test_implicit_gemm_convolution(ops, dev, B, H, W, C, Cout, R, pad):
                                                 (33, 10, 10, 64, 64, 1, 0)])
 def test_implicit_gemm_convolution_stride2(ops, dev, B, H, W, C, Cout, R, pad):
     """Stride 2 (the first 3x3 and the 1x1 downsample of layer2-4): forward and weight gradient gather strided pixel
-    boxes (TMA element strides); the input gradient of these layers stays on the explicit GEMM + col2im path."""
+    boxes (TMA element strides); the input gradient runs as one implicit GEMM per parity class of the dx pixels."""
     _implicit_conv_case(ops, dev, B, H, W, C, Cout, R, pad, 2)
 
 
@@ -288,9 +288,8 @@ def _implicit_conv_case(ops, dev, B, H, W, C, Cout, R, pad, stride):
     dy = rnd(dev, B, Cout, Ho, Wo)
     ref.backward(dy.double().cpu())
     dyn = dy.permute(0, 2, 3, 1).contiguous()
-    if stride == 1:
-        dx = ops.conv_dgrad(dyn, wm, H, W, C, R, R, pad)
-        close(dx.permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 2e-3)
+    dx = ops.conv_dgrad(dyn, wm, H, W, C, R, R, pad, stride)
+    close(dx.permute(0, 3, 1, 2), xf.grad, 2 * BF16_EPS, 2e-3)
     dw = ops.conv_wgrad(dyn, xn, R, R, pad, stride)
     close(dw.view(Cout, R, R, C).permute(0, 3, 1, 2), wf.grad, 1e-4, 1e-2)
 
