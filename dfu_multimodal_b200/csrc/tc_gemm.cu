@@ -249,6 +249,7 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 // direct-store path for outputs TMA cannot describe) is ~11k SASS instructions and its warps stall on instruction
 // fetch (ncu: no_inst); the shapes that carry the step get instantiations with the flags folded at compile time:
 //   1 bf16 store   2 bf16 + bias   3 bf16 + bias + residual   4 bf16 + bias + GELU + pre-activation copy   5 fp32 store
+//   6 bf16 x residual operand (stored GELU')   7 bf16 + bias + GELU, aux = GELU'   8 bf16 + residual (no bias)
 // CG: 1 = one CTA per 128-row tile; 2 = a CTA pair (cluster of 2) shares a 256-row tile: tcgen05.mma.cta_group::2 issued by
 //     the even CTA, each CTA staging its 128 rows of A and HALF of the B tile, so every SM pulls a third less operand data
 //     per FLOP through its L2 port -- the limit of the 128x256 single-CTA kernel on the K >= 768 shapes.
@@ -471,7 +472,7 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const bool f_fp32 = GEN ? (p.d_fp32 != 0) : (EM == 5);
         const bool f_bias = GEN ? (p.bias != nullptr) : ((EM >= 2 && EM <= 4) || EM == 7);
         const int f_act = GEN ? p.act : (EM == 4 ? 2 : EM == 6 ? 5 : EM == 7 ? 4 : 0);
-        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3 || EM == 6);
+        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3 || EM == 6 || EM == 8);
         const bool f_aux = GEN ? (p.aux != nullptr) : (EM == 4 || EM == 7);
         const float alpha = GEN ? p.alpha : 1.f;
         const int quarter = warp_idx & 3;        // TMEM lane quarter this warp may touch
@@ -1065,6 +1066,7 @@ cudaError_t set_smem_attrs() {
     DFU_SET_ATTR(false, 5, 2);
     DFU_SET_ATTR(false, 6, 1); DFU_SET_ATTR(false, 6, 2); DFU_SET_ATTR(true, 6, 1); DFU_SET_ATTR(true, 6, 2);
     DFU_SET_ATTR(false, 7, 1); DFU_SET_ATTR(false, 7, 2);
+    DFU_SET_ATTR(false, 8, 1); DFU_SET_ATTR(false, 8, 2);
 #undef DFU_SET_ATTR
     return e;
 }
@@ -1087,6 +1089,7 @@ int pick_epilogue_mode(const GemmParams& p) {
     if (bias && !res && aux && p.act == 2) return 4;
     if (!bias && res && !aux && p.act == 5) return 6;
     if (bias && !res && aux && p.act == 4) return 7;
+    if (!bias && res && !aux && p.act == 0) return 8;      // D = AB + res: the skip gradient joins in the dgrad epilogue
     return 0;
 }
 
@@ -1120,6 +1123,7 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
             case 6: launch_pair<6>(grid, stream, ma, mb, md, mx, p); return;
             case -6: launch_pair<6, true>(grid, stream, ma, mb, md, mx, p); return;
             case 7: launch_pair<7>(grid, stream, ma, mb, md, mx, p); return;
+            case 8: launch_pair<8>(grid, stream, ma, mb, md, mx, p); return;
             default: launch_pair<5>(grid, stream, ma, mb, md, mx, p); return;
         }
     }
@@ -1134,6 +1138,7 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
         case 6: dfu_tc_gemm_kernel<false, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case -6: dfu_tc_gemm_kernel<true, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 7: dfu_tc_gemm_kernel<false, 7, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 8: dfu_tc_gemm_kernel<false, 8, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         default: dfu_tc_gemm_kernel<false, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
     }
 }
