@@ -155,3 +155,57 @@ def test_device_prefetcher_has_no_cpu_path():
     from dfu_multimodal_b200.data import DevicePrefetcher
     with pytest.raises(RuntimeError):
         DevicePrefetcher(iter([]), "cpu")
+
+
+def test_kernel_selection_predicates_cover_every_resnet_convolution():
+    """Which convolutions take the implicit-GEMM entry point (dfu_conv_gemm) and which shapes the epilogue statistics
+    serve: every 3x3 and every strided convolution of ResNet50 except the 3-channel stem; 1x1/s1 is a plain GEMM."""
+    from dfu_multimodal_b200 import ops
+    ops.set_conv_impl("implicit")
+    m = D.DfuResNet50()
+    implicit = direct = explicit = 0
+    for name, mod in m.named_modules():
+        if not isinstance(mod, D.nn.DfuConv2d):
+            continue
+        Cout, C, R, S = mod.weight.shape
+        stride = mod.stride[0]
+        if ops.conv_implicit_ok(C, Cout, R, S, stride):
+            implicit += 1
+            assert R * S > 1 or stride == 2, name
+        elif R == 1 and S == 1 and stride == 1:
+            direct += 1
+        else:
+            explicit += 1
+            assert name == "conv1", name             # only the stem goes through an im2col matrix
+        assert ops.colstats_ok(Cout, mode=2), name   # BatchNorm sums of every layer come from the GEMM epilogue
+    assert (implicit, direct, explicit) == (16 + 3, 33, 1)
+    assert ops.colstats_ok(3072, mode=1) and not ops.colstats_ok(3072, mode=2)      # fc1 bias gradient: sums only
+    ops.set_conv_impl("im2col")
+    try:
+        assert not ops.conv_implicit_ok(64, 64, 3, 3, 1)
+    finally:
+        ops.set_conv_impl("implicit")
+
+
+def test_abi_rejects_unsupported_convolution_and_epilogue_combinations_without_a_device():
+    """Argument validation happens before any CUDA call, so the error contract is testable on the CPU."""
+    import ctypes
+    from dfu_multimodal_b200 import _lib
+    L = _lib.load()
+    a = _lib.ConvArgs()
+    a.mode, a.B, a.H, a.W, a.C, a.Cout, a.R, a.S, a.stride, a.pad = 1, 1, 8, 8, 48, 64, 3, 3, 1, 1      # C % 64 != 0
+    assert L.dfu_conv_gemm(ctypes.byref(a), None) != 0
+    assert b"multiples of 64" in L.dfu_last_error()
+    a.C, a.stride = 64, 3
+    assert L.dfu_conv_gemm(ctypes.byref(a), None) != 0
+    assert b"stride" in L.dfu_last_error()
+    g = _lib.GemmArgs()
+    g.M = g.N = g.K = 64
+    g.nb0 = g.nb1 = 1
+    g.A = g.B = g.D = 16
+    g.act = 5                                            # D *= res needs res
+    assert L.dfu_gemm(ctypes.byref(g), None) != 0
+    assert b"act=5" in L.dfu_last_error()
+    g.act = 4                                            # GELU with derivative output needs aux
+    assert L.dfu_gemm(ctypes.byref(g), None) != 0
+    assert b"act=4" in L.dfu_last_error()
