@@ -88,7 +88,10 @@ class FusedAdamW(torch.optim.Optimizer):
                     g = p.grad
                     if g is None:
                         continue
-                    if g.dtype != torch.float32 or g.stride() != p.stride():
+                    # same element order in memory?  strides of size-1 dims are arbitrary (a 1x1 convolution's weight
+                    # gradient arrives as (C,1,C,C) against the parameter's (C,1,1,1)) and must not force a copy
+                    same_order = all(gs == ps for gs, ps, n in zip(g.stride(), p.stride(), p.shape) if n > 1)
+                    if g.dtype != torch.float32 or g.shape != p.shape or not same_order:
                         g2 = torch.empty_like(p, memory_format=torch.preserve_format)
                         g2.copy_(g)
                         g = g2
