@@ -79,6 +79,10 @@ def cpu_reference_run(steps, warmup, batch=16):
     host cores, all threads.  Bounded sample: `batch` pairs per step."""
     import torch
     from oracle import reference_model as R
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and gets all usable cores back
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if "LOCAL_RANK" in os.environ and torch.get_num_threads() < usable:
+        torch.set_num_threads(usable)
     threads = torch.get_num_threads()
     model = R.seeded_init_(R.OracleFusion(), 0, calibrate=False)
     rgb_u8, th_u8, labels = R.synthetic_batch(batch, 0)
