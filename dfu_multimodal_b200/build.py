@@ -1,5 +1,6 @@
 """Builds libdfu_b200.so (sm_100a only) in-tree with nvcc.  No torch headers are involved: the library is a
 plain C-ABI shared object (include/dfu_b200.h) that the host side binds with ctypes."""
+import glob
 import hashlib
 import os
 import shutil
@@ -14,10 +15,10 @@ STAMP = os.path.join(HERE, ".libdfu_b200.stamp")
 SOURCES = ["api.cu", "tc_gemm.cu", "layout.cu", "norm.cu", "pointwise.cu", "train_misc.cu", "attention.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-# erff/expf accuracy matters for GELU parity; fast-math only affects intrinsics we call explicitly, so drop it.
-NVCC_FLAGS.remove("--use_fast_math")
+# no --use_fast_math: erff / expf accuracy matters for GELU and softmax parity; fast intrinsics are called explicitly
+# where the kernels want them.
 
 
 def _nvcc():
@@ -29,8 +30,9 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    paths = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
-                                                       os.path.join(HERE, "..", "include", "dfu_b200.h")]
+    # every source and header under csrc/ (tc_common.cuh is included by attention.cu and tc_gemm.cu) plus the public ABI
+    paths = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")))
+    paths.append(os.path.join(HERE, "..", "include", "dfu_b200.h"))
     for p in paths:
         if os.path.exists(p):
             with open(p, "rb") as f:

@@ -52,6 +52,7 @@ class GradBucketer:
                 off += (p.numel() + 7) // 8 * 8
         self.pending = [0] * len(self.buckets)
         self.producers = [set() for _ in self.buckets]
+        self.got = set()          # parameters that produced a gradient since begin_step()
         self.works = []
         self.is_cuda = params[0].is_cuda
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream() if self.is_cuda else None)
@@ -61,10 +62,12 @@ class GradBucketer:
     def begin_step(self):
         self.pending = [len(b) for b in self.buckets]
         self.producers = [set() for _ in self.buckets]
+        self.got = set()
         self.works = []
 
     def _on_grad(self, p):
         bi, off, n = self.slot[p]
+        self.got.add(p)
         g = p.grad
         if g.stride() != p.stride():
             g = g.contiguous() if p.is_contiguous() else torch.empty_like(p).copy_(g)
@@ -93,7 +96,14 @@ class GradBucketer:
     def finish_step(self):
         """All buckets reduced and visible to the current stream."""
         for bi, left in enumerate(self.pending):
-            if left > 0:                 # parameters that received no gradient this step: reduce what is there
+            if left > 0:
+                # some parameters of this bucket received no gradient this step (frozen or conditionally used): their
+                # slices still hold LAST step's reduced gradient -- clear them so the all-reduce moves zeros, and
+                # grad_source() reports them as gradient-less so the optimizer skips them like torch.optim.AdamW does
+                for p in self.buckets[bi]:
+                    if p not in self.got:
+                        _, off, n = self.slot[p]
+                        self.flat[bi][off:off + n].zero_()
                 self.pending[bi] = 0
                 self._launch(bi)
         if self.is_cuda:
@@ -106,7 +116,7 @@ class GradBucketer:
 
     def grad_source(self, p):
         """For FusedAdamW.set_grad_source: (bf16 grad slice, is_bf16, scale)."""
-        if p not in self.slot:
+        if p not in self.slot or p not in self.got:
             return None
         bi, off, n = self.slot[p]
         scale = 1.0

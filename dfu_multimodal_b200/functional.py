@@ -564,8 +564,13 @@ _DROPOUT_SITE = [0]
 
 
 class DropoutFn(Function):
+    """nn.Dropout in train(): every call draws a fresh mask.  The device-resident counter is advanced by a 1-thread
+    kernel right before the mask kernel of the same call (same stream), so eager loops written like the reference's
+    (train_multimodal_fusion.py:374-380) and CUDA-graph replays both see a new mask per call."""
+
     @staticmethod
     def forward(ctx, x, p, site):
+        ops.DROPOUT.tick(x.device)
         y, mask = ops.dropout(x.contiguous(), p, site)
         ctx.p = p
         ctx.save_for_backward(mask)

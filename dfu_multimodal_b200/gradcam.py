@@ -1,9 +1,20 @@
-"""Grad-CAM (a11) with the same observable behaviour as the reference class
-(notebooks/grad_cam_visualization.py:327-429), including its quirks: forward hooks on every
-module whose name contains a target string, score = output[0, 0] (class_idx is ignored), the LAST matching module
-name supplies activations and gradients, channel count min(C_A, C_G), and an input-gradient saliency fallback for
-non-4D activations (the ViT branch).  The reduction itself runs in one kernel (dfu_gradcam / dfu_saliency) instead
-of the reference's per-channel Python loop (:421-422)."""
+"""Grad-CAM (a11) with the observable behaviour of the reference's class (notebooks/grad_cam_visualization.py:327-429),
+quirks included:
+
+  * the target is the LAST module of `model.named_modules()` whose name contains one of the target strings
+    (`layer4` -> `layer4.2.relu`; `blocks` -> `blocks.11.mlp.fc2`);
+  * the activation is what that module returned on its LAST forward call of the pass, the gradient is the one that
+    reached any of its outputs LAST during backward (for the shared `layer4.2.relu` that is the 512-channel gradient of
+    its first call against the 2048-channel activation of its third);
+  * the score is `output[0, 0]` whatever `class_idx` says; `min(C_A, C_G)` channels are reduced;
+  * activations that are not 4-D (the ViT branch) fall back to the input-gradient saliency map.
+
+The plumbing is not the reference's: only the ONE resolved target module is hooked (the reference hooks all 28 matching
+modules and keeps two name-keyed dictionaries), so only the Bottleneck that owns it leaves the fused path, and one
+"latest activation" / "latest gradient" slot each replace the dictionaries.  The reduction runs in one kernel per sample
+(dfu_gradcam / dfu_saliency) instead of a Python loop over channels (:421-422), and `generate_cam_batch` produces the
+maps of a whole batch from ONE forward + backward pass (eval-mode samples are independent, so the gradient of
+sum_i output[i, 0] is every sample's own gradient)."""
 import torch
 
 from . import ops
@@ -12,61 +23,75 @@ from . import ops
 class GradCAM:
     def __init__(self, model, target_layers):
         self.model = model
-        self.target_layers = target_layers if isinstance(target_layers, list) else [target_layers]
-        self.activations = {}
-        self.gradients = {}
-        self._handles = []
-        self._register_hooks()
+        self.target_layers = list(target_layers) if isinstance(target_layers, (list, tuple)) else [target_layers]
+        self.target_name, self.target_module = None, None
+        for name, module in model.named_modules():
+            if any(t in name for t in self.target_layers):
+                self.target_name, self.target_module = name, module          # the last match wins
+        self._act = None        # latest forward output of the target
+        self._grad = None       # latest gradient that reached one of its outputs
+        self._handle = None
+        if self.target_module is not None:
+            self._handle = self.target_module.register_forward_hook(self._on_forward)
 
-    def _register_hooks(self):
-        def get_activation(name):
-            def hook(module, inputs, output):
-                self.activations[name] = output
-                if isinstance(output, torch.Tensor) and output.requires_grad:
-                    def save_grad(grad):
-                        self.gradients[name] = grad
-                    output.register_hook(save_grad)
-            return hook
+    # -- hooks ---------------------------------------------------------------------------------------------
+    def _on_forward(self, module, inputs, output):
+        self._act = output
+        if isinstance(output, torch.Tensor) and output.requires_grad:
+            output.register_hook(self._on_grad)
 
-        for name, module in self.model.named_modules():
-            if any(layer in name for layer in self.target_layers):
-                self._handles.append(module.register_forward_hook(get_activation(name)))
+    def _on_grad(self, grad):
+        self._grad = grad
 
     def close(self):
-        """The reference never removes its hooks (a new GradCAM per sample piles them up); we offer a way out."""
-        for h in self._handles:
-            h.remove()
-        self._handles = []
+        """The reference never removes its hooks (a new GradCAM per sample piles them up); this does."""
+        if self._handle is not None:
+            self._handle.remove()
+            self._handle = None
 
-    def generate_cam(self, input_tensor, class_idx=None):
-        """input (1,C,H,W) -> numpy heat map: (h,w) of the target layer for 4-D activations, else (H,W) saliency."""
+    # -- one pass --------------------------------------------------------------------------------------------
+    def _pass(self, inputs):
         self.model.eval()
-        x = input_tensor.clone().detach().requires_grad_(True)
+        self._act = self._grad = None
+        x = inputs.clone().detach().requires_grad_(True)
         with torch.enable_grad():
-            output = self.model(x)
+            out = self.model(x)
             self.model.zero_grad()
-            score = output[0, 0]
-            score.backward()
+            out[:, 0].sum().backward()         # batch 1: exactly output[0, 0] (grad_cam_visualization.py:385-386)
+        return x
 
-        layer_name = None
-        for name, _ in self.model.named_modules():
-            if any(layer in name for layer in self.target_layers):
-                layer_name = name
-        if layer_name is None:
-            return None
-        act = self.activations[layer_name]
-        grad = self.gradients.get(layer_name, None)
-
+    def _maps(self, x, n):
+        """List of n numpy maps from the slots filled by _pass."""
+        act, grad = self._act, self._grad
+        if act is None:
+            return [None] * n
+        hw_in = tuple(x.shape[2:])
         if act.ndim != 4 or grad is None or grad.ndim != 4:
             if x.grad is None:
-                return torch.zeros(input_tensor.shape[2:]).numpy()
-            return ops.saliency(x.grad.detach()[0]).cpu().numpy()
-
-        a = ops.as_nhwc(act.detach())[0]
-        g = ops.as_nhwc(grad.detach())[0]
-        h, w, ca = a.shape
-        cg = g.shape[2]
-        if g.shape[0] != h or g.shape[1] != w:
+                return [torch.zeros(hw_in).numpy() for _ in range(n)]
+            g = x.grad.detach()
+            return [ops.saliency(g[i]).cpu().numpy() for i in range(n)]
+        a = ops.as_nhwc(act.detach())
+        g = ops.as_nhwc(grad.detach())
+        _, h, w, ca = a.shape
+        cg = g.shape[3]
+        if g.shape[1] != h or g.shape[2] != w:
             raise RuntimeError("Grad-CAM activation/gradient spatial sizes differ: %s vs %s" % (a.shape, g.shape))
-        cam = ops.gradcam_reduce(a.reshape(h * w, ca), g.reshape(h * w, cg), min(ca, cg))
-        return cam.view(h, w).cpu().numpy()
+        nc = min(ca, cg)
+        cams = [ops.gradcam_reduce(a[i].reshape(h * w, ca), g[i].reshape(h * w, cg), nc).view(h, w) for i in range(n)]
+        return [c.numpy() for c in torch.stack(cams).cpu()]
+
+    def generate_cam(self, input_tensor, class_idx=None):
+        """input (1,C,H,W) -> numpy heat map: (h,w) of the target layer for 4-D activations, else (H,W) saliency.
+        `class_idx` is accepted and ignored, as in the reference."""
+        if self.target_module is None:
+            return None
+        x = self._pass(input_tensor)
+        return self._maps(x, 1)[0]
+
+    def generate_cam_batch(self, inputs):
+        """inputs (B,C,H,W) -> list of B maps, each equal to generate_cam(inputs[i:i+1]), from one forward + backward."""
+        if self.target_module is None:
+            return [None] * inputs.shape[0]
+        x = self._pass(inputs)
+        return self._maps(x, inputs.shape[0])

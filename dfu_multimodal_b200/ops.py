@@ -89,10 +89,13 @@ class _ZeroArena:
         self.off = 0
         self.need = 0
         self.active = False
+        self.retired = []       # outgrown buffers stay allocated: a captured CUDA graph may still clear and use them
 
     def begin_step(self, device):
         want = max(self.need, self.off)
         if self.buf is None or self.buf.numel() < want or self.buf.device != device:
+            if self.buf is not None:
+                self.retired.append(self.buf)
             self.buf = torch.empty(int(want * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
         self.need = want
         used = min(self.buf.numel(), max(want, 1))

@@ -17,9 +17,9 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
-        self._tables = {}      # group index -> cached device table
+        self._tables = {}      # (group index, pointer signature) -> cached device table
         self._grad_source = None
-        self._steps = {}
+        self._steps = {}       # (device type, index) -> fp32 device scalar shared by every parameter on that device
 
     def set_grad_source(self, source):
         """source(p) -> (tensor_with_grad_in_storage_order, is_bf16, scale): lets the data-parallel bucketer hand
@@ -63,18 +63,85 @@ class FusedAdamW(torch.optim.Optimizer):
                 torch.tensor(chunk_tensor, dtype=torch.int32).pin_memory(),
                 torch.tensor(chunk_offset, dtype=torch.int32).pin_memory()]
         table, ct, co = [h.to(dev, non_blocking=True) for h in host]
-        sig = tuple((p.data_ptr(), g.data_ptr(), getattr(p, "_dfu_shadow", (None, None))[1] is not None)
-                    for p, g in zip(params, grads))
-        # one shared device step counter per group (all params step together)
+        # one shared device step counter per device (all params step together)
         step = self.state[params[0]]["step"]
-        return dict(table=table, ct=ct, co=co, host=host, n=n, n_chunks=len(chunk_tensor), sig=sig, shadowed=shadowed, step=step,
-                    g_bf16=g_bf16)
+        return dict(table=table, ct=ct, co=co, host=host, n=n, n_chunks=len(chunk_tensor), shadowed=shadowed, step=step,
+                    g_bf16=g_bf16, captured=torch.cuda.is_current_stream_capturing())
+
+    def _signature(self, params, grads):
+        """Everything the device table bakes in: parameter, gradient, moment and shadow addresses."""
+        sig = []
+        for p, g in zip(params, grads):
+            st = self.state.get(p, {})
+            m, v = st.get("exp_avg"), st.get("exp_avg_sq")
+            sh = getattr(p, "_dfu_shadow", None)
+            sig.append((p.data_ptr(), g.data_ptr(), m.data_ptr() if m is not None else 0,
+                        v.data_ptr() if v is not None else 0, sh[1].data_ptr() if sh is not None else 0))
+        return tuple(sig)
+
+    def _table_for(self, gi, group, params, grads, g_bf16):
+        for p in params:
+            self._state_for(p)
+        key = (gi, self._signature(params, grads))
+        cached = self._tables.get(key)
+        if cached is None:
+            cached = self._build(gi, group, params, grads, g_bf16)
+            # tables built during CUDA-graph capture are baked into that graph (device table, pinned staging buffers) and
+            # must outlive it; eager tables are keyed by allocator-dependent gradient addresses, keep only a few
+            eager = [k for k, c in self._tables.items() if not c["captured"]]
+            for k in eager[:max(0, len(eager) - 3)]:
+                del self._tables[k]
+            self._tables[key] = cached
+        return cached
+
+    # ---------------------------------------------------------------------------------------------------- checkpoints
+    def state_dict(self):
+        """Same schema as torch.optim.AdamW's (train_multimodal_fusion.py:433-439 saves it as `optimizer_state_dict`):
+        per-parameter `step` as a CPU fp32 scalar tensor, `exp_avg`, `exp_avg_sq`, so a stock AdamW can load it."""
+        sd = super().state_dict()
+        sd["state"] = {k: dict(v) for k, v in sd["state"].items()}      # the base class hands out the live per-param dicts
+        host_steps = {k: v.detach().float().cpu() for k, v in self._steps.items()}
+        for st in sd["state"].values():
+            if "step" in st and torch.is_tensor(st["step"]):
+                dev = st["step"].device
+                st["step"] = host_steps.get((dev.type, dev.index), st["step"].detach().float().cpu()).clone()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """Accepts checkpoints of this class and of torch.optim.AdamW (any device, any memory layout of the moments):
+        `step` becomes the shared device counter, the moments are re-laid-out like their parameter (conv weights are
+        channels_last here, NCHW in a reference checkpoint), and every cached pointer table is dropped."""
+        super().load_state_dict(state_dict)
+        self._tables.clear()
+        self._steps = {}
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if not st:
+                    continue
+                key = (p.device.type, p.device.index)
+                step = st.get("step", 0.0)
+                step = float(step.item()) if torch.is_tensor(step) else float(step)
+                if key not in self._steps:
+                    self._steps[key] = torch.full((), step, dtype=torch.float32, device=p.device)
+                elif float(self._steps[key].item()) != step:
+                    raise RuntimeError("FusedAdamW keeps one step counter per device; the checkpoint holds different "
+                                       "step counts (%g vs %g)" % (float(self._steps[key].item()), step))
+                st["step"] = self._steps[key]
+                for name in ("exp_avg", "exp_avg_sq"):
+                    src = st.get(name)
+                    if src is None:
+                        src = torch.zeros((), dtype=torch.float32).expand(p.shape)
+                    dst = torch.empty_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+                    dst.copy_(src.to(p.device))
+                    st[name] = dst
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         L = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
+        ticked = set()         # the shared counter advances once per step() however many groups read it
         for gi, group in enumerate(self.param_groups):
             params, grads = [], []
             g_bf16, scale = False, 1.0
@@ -101,18 +168,18 @@ class FusedAdamW(torch.optim.Optimizer):
                 grads.append(g)
             if not params:
                 continue
-            cached = self._tables.get(gi)
-            sig = tuple((p.data_ptr(), g.data_ptr(), getattr(p, "_dfu_shadow", (None, None))[1] is not None)
-                        for p, g in zip(params, grads))
-            if cached is None or cached["sig"] != sig:
-                cached = self._build(gi, group, params, grads, g_bf16)
-                self._tables[gi] = cached
+            if len(set((p.device.type, p.device.index) for p in params)) > 1:
+                raise RuntimeError("FusedAdamW: the parameters of one group must live on one device")
+            cached = self._table_for(gi, group, params, grads, g_bf16)
             b1, b2 = group["betas"]
-            check(L.dfu_adamw_tick(cached["step"].data_ptr(), st), "adamw_tick")
+            if cached["step"].data_ptr() not in ticked:
+                ticked.add(cached["step"].data_ptr())
+                check(L.dfu_adamw_tick(cached["step"].data_ptr(), st), "adamw_tick")
+                ops._count()
             check(L.dfu_adamw(cached["table"].data_ptr(), cached["n"], cached["ct"].data_ptr(), cached["co"].data_ptr(),
                               cached["n_chunks"], CHUNK, cached["step"].data_ptr(), group["lr"], b1, b2, group["eps"],
                               group["weight_decay"], scale, 1 if cached["g_bf16"] else 0, st), "adamw")
-            ops._count(2)
+            ops._count()
             fresh = set(id(p) for p in cached["shadowed"])
             for p in params:
                 if id(p) in fresh:

@@ -10,24 +10,29 @@ from .functional import cross_entropy
 
 
 class TrainStep:
-    def __init__(self, model, optimizer, class_weights=None, use_graph=True, bucketer=None, warmup=3):
+    """Captured CUDA graphs are keyed by the batch's shapes and dtypes: the reference DataLoaders do not drop the last,
+    smaller batch of an epoch (train_multimodal_fusion.py:272-275), so a new shape gets its own graph (up to
+    `max_graphs`) and anything beyond that runs eagerly -- never a silent broadcast into the first batch's buffers."""
+
+    def __init__(self, model, optimizer, class_weights=None, use_graph=True, bucketer=None, warmup=3, max_graphs=3):
         self.model, self.optimizer, self.bucketer = model, optimizer, bucketer
         self.class_weights = class_weights
         self.use_graph = use_graph
         self.warmup = warmup
-        self.graph = None
-        self.static = None
+        self.max_graphs = max_graphs
+        self.graphs = {}            # (shape, dtype) signature of the batch -> (graph, static inputs, static outputs, launches)
+        self.graph = None           # the most recently replayed graph (None while running eagerly)
         self.calls = 0
         self.launches_per_step = None
 
     # -- the step itself (eager) -------------------------------------------------------------------------
-    def _step(self, rgb, thermal, labels):
+    def _step(self, *args):
+        *inputs, labels = args
         self.optimizer.zero_grad(set_to_none=True)
-        ops.ZERO_ARENA.begin_step(rgb.device)      # one dfu_zero launch clears every accumulator of the step
+        ops.ZERO_ARENA.begin_step(labels.device)   # one dfu_zero launch clears every accumulator of the step
         if self.bucketer is not None:
             self.bucketer.begin_step()
-        ops.DROPOUT.tick(rgb.device)
-        logits = self.model(rgb, thermal)
+        logits = self.model(*inputs)
         loss = cross_entropy(logits, labels, self.class_weights)
         loss.backward()
         if self.bucketer is not None:
@@ -36,69 +41,101 @@ class TrainStep:
         ops.ZERO_ARENA.end_step()
         return loss.detach(), logits.detach()
 
-    def _capture(self, rgb, thermal, labels):
-        self.static = (torch.empty_like(rgb), torch.empty_like(thermal), torch.empty_like(labels))
-        for s, t in zip(self.static, (rgb, thermal, labels)):
+    def _eager(self, *args):
+        n0 = ops.LAUNCHES
+        out = self._step(*args)
+        self.launches_per_step = ops.LAUNCHES - n0
+        return out
+
+    @staticmethod
+    def _key(*tensors):
+        return tuple((tuple(t.shape), t.dtype) for t in tensors)
+
+    def _capture(self, key, *args):
+        static = tuple(torch.empty_like(t) for t in args)
+        for s, t in zip(static, args):
             s.copy_(t)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES
-        with torch.cuda.graph(self.graph):
-            self.static_out = self._step(*self.static)
-        self.launches_per_step = ops.LAUNCHES - n0
+        with torch.cuda.graph(graph):
+            static_out = self._step(*static)
+        self.graphs[key] = (graph, static, static_out, ops.LAUNCHES - n0)
+        return self.graphs[key]
 
-    def __call__(self, rgb, thermal, labels):
-        """rgb/thermal: device tensors (uint8 NHWC or fp32 NCHW); labels int64. Returns (loss, logits) on device."""
+    def __call__(self, *args):
+        """ts(rgb, thermal, labels) for the fusion model, ts(images, labels) for a single-modality model.  Inputs are
+        device tensors (uint8 NHWC or fp32 NCHW), labels int64.  Returns (loss, logits) on the device."""
         self.model.train()
+        if len(args) < 2:
+            raise RuntimeError("TrainStep: expected (*model_inputs, labels)")
+        if any(t.shape[0] != args[-1].shape[0] for t in args):
+            raise RuntimeError("TrainStep: batch sizes differ: %s" % ([int(t.shape[0]) for t in args],))
         if not self.use_graph:
-            n0 = ops.LAUNCHES
-            out = self._step(rgb, thermal, labels)
-            self.launches_per_step = ops.LAUNCHES - n0
-            return out
-        if self.graph is None:
-            if self.calls < self.warmup:
-                # eager warm-up: allocates optimizer state and weight shadows, fills the allocator pools
+            self.graph = None
+            return self._eager(*args)
+        key = self._key(*args)
+        entry = self.graphs.get(key)
+        if entry is None:
+            if self.calls < self.warmup or len(self.graphs) >= self.max_graphs:
+                # eager: the warm-up calls allocate optimizer state and weight shadows and fill the allocator pools;
+                # later, batch shapes beyond the graph budget simply run uncaptured
                 self.calls += 1
-                n0 = ops.LAUNCHES
-                out = self._step(rgb, thermal, labels)
-                self.launches_per_step = ops.LAUNCHES - n0
-                return out
-            self._capture(rgb, thermal, labels)
-        for s, t in zip(self.static, (rgb, thermal, labels)):
+                self.graph = None
+                return self._eager(*args)
+            entry = self._capture(key, *args)
+        graph, static, static_out, launches = entry
+        for s, t in zip(static, args):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
-        self.graph.replay()
-        return self.static_out
+        graph.replay()
+        ops._count(launches)          # replayed kernels count like launched ones (bench.py's gpu_launches)
+        self.graph, self.launches_per_step = graph, launches
+        return static_out
 
 
 class EvalStep:
-    """Inference forward (extended_metrics.py:623-642) with the softmax/argmax epilogue kernel; graph-captured."""
+    """Inference forward (extended_metrics.py:623-642) with the softmax/argmax epilogue kernel; one captured CUDA graph
+    per batch shape (the last batch of a loader is smaller)."""
 
-    def __init__(self, model, use_graph=True):
-        self.model, self.use_graph = model, use_graph
+    def __init__(self, model, use_graph=True, max_graphs=4):
+        self.model, self.use_graph, self.max_graphs = model, use_graph, max_graphs
+        self.graphs = {}
         self.graph = None
+        self.launches_per_step = None
 
     @torch.no_grad()
-    def _fwd(self, rgb, thermal):
-        logits = self.model(rgb, thermal)
+    def _fwd(self, *inputs):
+        logits = self.model(*inputs)
         prob1, pred = ops.predict(logits)
         return logits, prob1, pred
 
-    def __call__(self, rgb, thermal):
+    def __call__(self, *inputs):
+        """step(rgb, thermal) or step(images): (logits [B,C] fp32, softmax[:,1] [B] fp32, argmax [B] int64), on the device."""
         self.model.eval()
-        if not self.use_graph:
-            return self._fwd(rgb, thermal)
-        if self.graph is None or self.static[0].shape != rgb.shape:
-            self._fwd(rgb, thermal)      # warm-up (weight shadows, allocator)
-            self.static = (torch.empty_like(rgb), torch.empty_like(thermal))
-            for s, t in zip(self.static, (rgb, thermal)):
+        if any(t.shape[0] != inputs[0].shape[0] for t in inputs):
+            raise RuntimeError("EvalStep: batch sizes differ: %s" % ([int(t.shape[0]) for t in inputs],))
+        key = TrainStep._key(*inputs)
+        entry = self.graphs.get(key) if self.use_graph else None
+        if entry is None:
+            if not self.use_graph or len(self.graphs) >= self.max_graphs:
+                self.graph = None
+                return self._fwd(*inputs)
+            self._fwd(*inputs)           # warm-up (weight shadows, allocator)
+            static = tuple(torch.empty_like(t) for t in inputs)
+            for s, t in zip(static, inputs):
                 s.copy_(t)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.static_out = self._fwd(*self.static)
-        for s, t in zip(self.static, (rgb, thermal)):
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                static_out = self._fwd(*static)
+            entry = self.graphs[key] = (graph, static, static_out, ops.LAUNCHES - n0)
+        graph, static, static_out, launches = entry
+        for s, t in zip(static, inputs):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
-        self.graph.replay()
-        return self.static_out
+        graph.replay()
+        ops._count(launches)
+        self.graph, self.launches_per_step = graph, launches
+        return static_out

@@ -84,3 +84,28 @@ def test_bucket_layout_is_aligned_and_reverse_ordered():
         bi, off, n = b.slot[p]
         assert off % 8 == 0 and n == p.numel()      # 16-byte aligned bf16 slices
     b.remove()
+
+
+def test_parameter_without_gradient_is_skipped_not_given_a_stale_one():
+    """A parameter that gets no gradient in a step must not be handed last step's reduced gradient."""
+    model = _model()
+    extra = nn.Linear(32, 2)
+    params = list(model.parameters()) + list(extra.parameters())
+    b = GradBucketer(params, bucket_bytes=1 << 20, cast_fn=_cpu_cast)
+    x = torch.randn(4, 16)
+    h = model[:-1](x)
+    b.begin_step()
+    (model[-1](h) + extra(h)).sum().backward()          # step 1: everyone gets a gradient
+    b.finish_step()
+    assert all(b.grad_source(p) is not None for p in params)
+    assert float(b.grad_source(extra.weight)[0].float().abs().max()) > 0
+    for p in params:
+        p.grad = None
+    b.begin_step()
+    model(x).sum().backward()                            # step 2: `extra` is not used
+    b.finish_step()
+    assert b.grad_source(extra.weight) is None and b.grad_source(extra.bias) is None
+    bi, off, n = b.slot[extra.weight]
+    assert float(b.flat[bi][off:off + n].float().abs().max()) == 0.0
+    assert b.grad_source(model[0].weight) is not None
+    b.remove()

@@ -551,3 +551,112 @@ def test_fused_adamw_matches_torch_adamw(dev):
         b.step()
     for p, q in zip(ps, qs):
         close(p, q, 1e-5, 1e-6)
+
+
+def test_fused_adamw_state_dict_roundtrips_with_torch_adamw(dev, tmp_path):
+    """train_multimodal_fusion.py:433-451 saves optimizer.state_dict(); resuming must work in both directions: FusedAdamW ->
+    file -> FusedAdamW, torch.optim.AdamW -> file (map_location cpu, NCHW moments) -> FusedAdamW, and FusedAdamW -> stock AdamW."""
+    from dfu_multimodal_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    shapes = [(64, 32, 3, 3), (256,), (300, 70), (1, 197, 8)]
+
+    def make(channels_last):
+        ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+        if channels_last:
+            ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+        return ps
+
+    def grads(step):
+        g = torch.Generator().manual_seed(100 + step)
+        return [torch.randn(s, generator=g).to(dev) for s in shapes]
+
+    def run(opt, ps, steps):
+        for st in steps:
+            for p, g in zip(ps, grads(st)):
+                p.grad = g.clone()
+            opt.step()
+
+    # uninterrupted stock run: the truth
+    truth = make(False)
+    run(torch.optim.AdamW(truth, lr=1e-3, weight_decay=1e-2), truth, range(6))
+
+    # (a) stock AdamW for 3 steps -> checkpoint on the CPU -> FusedAdamW (channels_last conv weight) for 3 more
+    a = make(False)
+    oa = torch.optim.AdamW(a, lr=1e-3, weight_decay=1e-2)
+    run(oa, a, range(3))
+    torch.save({"optimizer_state_dict": oa.state_dict(), "params": [p.detach().cpu() for p in a]}, tmp_path / "stock.pt")
+    ck = torch.load(tmp_path / "stock.pt", map_location="cpu")
+    b = make(True)
+    with torch.no_grad():
+        for p, q in zip(b, ck["params"]):
+            p.copy_(q)
+    ob = FusedAdamW(b, lr=1e-3, weight_decay=1e-2)
+    ob.load_state_dict(ck["optimizer_state_dict"])
+    assert ob.state[b[0]]["step"].is_cuda and ob.state[b[0]]["exp_avg"].stride() == b[0].stride()
+    run(ob, b, range(3, 6))
+    for p, q in zip(b, truth):
+        close(p, q, 1e-5, 1e-6)
+
+    # (b) FusedAdamW -> file -> a fresh FusedAdamW, after the first one has already stepped (stale pointer tables must go)
+    torch.save(ob.state_dict(), tmp_path / "fused.pt")
+    sd = torch.load(tmp_path / "fused.pt", map_location="cpu")
+    assert all(not st["step"].is_cuda and float(st["step"]) == 6.0 for st in sd["state"].values())
+    c = make(True)
+    with torch.no_grad():
+        for p, q in zip(c, b):
+            p.copy_(q)
+    oc = FusedAdamW(c, lr=1e-3, weight_decay=1e-2)
+    run(oc, c, [50])                                   # a step with its own state first ...
+    with torch.no_grad():
+        for p, q in zip(c, b):
+            p.copy_(q)
+    oc.load_state_dict(sd)                             # ... then the loaded state replaces it
+    run(ob, b, [6])
+    run(oc, c, [6])
+    for p, q in zip(c, b):
+        close(p, q, 1e-6, 1e-7)
+
+    # (c) and a stock AdamW can resume from a FusedAdamW checkpoint
+    d = [torch.nn.Parameter(p.detach().clone()) for p in c]
+    od = torch.optim.AdamW(d, lr=1e-3, weight_decay=1e-2)
+    od.load_state_dict(oc.state_dict())
+    run(od, d, [7])
+    run(oc, c, [7])
+    for p, q in zip(c, d):
+        close(p, q, 1e-5, 1e-6)
+
+
+def test_two_param_groups_share_one_step_count(dev):
+    """One device counter, ticked once per step() however many groups there are (bias correction must use t, not G*t)."""
+    from dfu_multimodal_b200.optim import FusedAdamW
+    torch.manual_seed(2)
+    ps = [torch.nn.Parameter(torch.randn(50, 20, device=dev)), torch.nn.Parameter(torch.randn(33, device=dev))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    a = FusedAdamW([{"params": [ps[0]]}, {"params": [ps[1]], "weight_decay": 0.0}], lr=1e-3, weight_decay=1e-2)
+    b = torch.optim.AdamW([{"params": [qs[0]]}, {"params": [qs[1]], "weight_decay": 0.0}], lr=1e-3, weight_decay=1e-2)
+    for _ in range(4):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        close(p, q, 1e-5, 1e-6)
+
+
+def test_dropout_module_draws_a_new_mask_on_every_call(dev):
+    """nn.Dropout semantics in an eager loop written like the reference's (no TrainStep): each call, a fresh mask."""
+    from dfu_multimodal_b200.nn import DfuDropout
+    drop = DfuDropout(0.5).train()
+    x = torch.ones(64, 512, device=dev, dtype=torch.bfloat16)
+    masks = [(drop(x) != 0) for _ in range(3)]
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert abs(masks[0].float().mean().item() - 0.5) < 0.02
+    g = torch.cuda.CUDAGraph()                          # and under CUDA-graph replay as well
+    y = drop(x)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        y = drop(x)
+    g.replay(); torch.cuda.synchronize(); m1 = (y != 0).clone()
+    g.replay(); torch.cuda.synchronize(); m2 = (y != 0).clone()
+    assert not torch.equal(m1, m2)
