@@ -35,6 +35,20 @@ class ConvArgs(ctypes.Structure):
         ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("ldw", ctypes.c_int64), ("dy", ctypes.c_void_p),
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64), ("accumulate", ctypes.c_int32), ("max_ctas", ctypes.c_int32),
         ("colstats", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p), ("act", ctypes.c_int32),
+    ]
+
+
+class V32GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("nb0", ctypes.c_int32), ("nb1", ctypes.c_int32),
+        ("A", ctypes.c_void_p), ("a_row_stride", ctypes.c_int64), ("a_col_stride", ctypes.c_int64), ("sa0", ctypes.c_int64), ("sa1", ctypes.c_int64),
+        ("B", ctypes.c_void_p), ("b_row_stride", ctypes.c_int64), ("b_col_stride", ctypes.c_int64), ("sb0", ctypes.c_int64), ("sb1", ctypes.c_int64),
+        ("D", ctypes.c_void_p), ("ldd", ctypes.c_int64), ("sd0", ctypes.c_int64), ("sd1", ctypes.c_int64),
+        ("bias", ctypes.c_void_p),
+        ("res", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("sr0", ctypes.c_int64), ("sr1", ctypes.c_int64),
+        ("alpha", ctypes.c_float),
+        ("act", ctypes.c_int32),
     ]
 
 

@@ -543,6 +543,19 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __res
 
 bool bn_shape_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0; }
 
+// Eval-mode BatchNorm folded into the preceding convolution's weights: one block per output channel.
+__global__ void __launch_bounds__(128) fold_bn_weights_kernel(const float* __restrict__ w, int K, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ mean,
+                                                              const float* __restrict__ var, float eps, bf16* __restrict__ w_out,
+                                                              long long ldo, float* __restrict__ bias_out) {
+    const int co = blockIdx.x;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    const float* wr = w + (long long)co * K;
+    bf16* orow = w_out + (long long)co * ldo;
+    for (int k = threadIdx.x; k < (int)ldo; k += blockDim.x) orow[k] = __float2bfloat16(k < K ? wr[k] * scale : 0.f);
+    if (threadIdx.x == 0) bias_out[co] = beta[co] - mean[co] * scale;
+}
+
 }  // namespace
 
 extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, void* stream) {
@@ -665,5 +678,13 @@ extern "C" int dfu_softmax_rows_bwd(const void* p, const void* dp, void* ds, int
     softmax_rows_bwd_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)p, (const bf16*)dp,
                                                                                           (bf16*)ds, rows, n, ld, scale);
     DFU_CHECK_LAUNCH("softmax_rows_bwd");
+    return DFU_OK;
+}
+
+extern "C" int dfu_fold_bn_weights(const float* w, int32_t Cout, int32_t K, const float* gamma, const float* beta, const float* mean,
+                                   const float* var, float eps, void* w_out, int64_t ldo, float* bias_out, void* stream) {
+    DFU_CHECK_ARG(w && gamma && beta && mean && var && w_out && bias_out && Cout > 0 && K > 0 && ldo >= K, "dfu_fold_bn_weights: bad args");
+    fold_bn_weights_kernel<<<Cout, 128, 0, (cudaStream_t)stream>>>(w, K, gamma, beta, mean, var, eps, (bf16*)w_out, ldo, bias_out);
+    DFU_CHECK_LAUNCH("dfu_fold_bn_weights");
     return DFU_OK;
 }

@@ -250,6 +250,7 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const void* v) {
 // fetch (ncu: no_inst); the shapes that carry the step get instantiations with the flags folded at compile time:
 //   1 bf16 store   2 bf16 + bias   3 bf16 + bias + residual   4 bf16 + bias + GELU + pre-activation copy   5 fp32 store
 //   6 bf16 x residual operand (stored GELU')   7 bf16 + bias + GELU, aux = GELU'   8 bf16 + residual (no bias)
+//   9 bf16 + bias + ReLU   10 bf16 + bias + residual, ReLU after the add (9 / 10: eval-mode conv with BatchNorm folded in)
 // CG: 1 = one CTA per 128-row tile; 2 = a CTA pair (cluster of 2) shares a 256-row tile: tcgen05.mma.cta_group::2 issued by
 //     the even CTA, each CTA staging its 128 rows of A and HALF of the B tile, so every SM pulls a third less operand data
 //     per FLOP through its L2 port -- the limit of the 128x256 single-CTA kernel on the K >= 768 shapes.
@@ -470,9 +471,9 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         constexpr bool GEN = (EM == 0);
         const bool f_tma = GEN ? (p.tma_store != 0) : true;
         const bool f_fp32 = GEN ? (p.d_fp32 != 0) : (EM == 5);
-        const bool f_bias = GEN ? (p.bias != nullptr) : ((EM >= 2 && EM <= 4) || EM == 7);
-        const int f_act = GEN ? p.act : (EM == 4 ? 2 : EM == 6 ? 5 : EM == 7 ? 4 : 0);
-        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3 || EM == 6 || EM == 8);
+        const bool f_bias = GEN ? (p.bias != nullptr) : ((EM >= 2 && EM <= 4) || EM == 7 || EM == 9 || EM == 10);
+        const int f_act = GEN ? p.act : (EM == 4 ? 2 : EM == 6 ? 5 : EM == 7 ? 4 : EM == 9 ? 1 : EM == 10 ? 6 : 0);
+        const bool f_res = GEN ? (p.res != nullptr) : (EM == 3 || EM == 6 || EM == 8 || EM == 10);
         const bool f_aux = GEN ? (p.aux != nullptr) : (EM == 4 || EM == 7);
         const float alpha = GEN ? p.alpha : 1.f;
         const int quarter = warp_idx & 3;        // TMEM lane quarter this warp may touch
@@ -640,6 +641,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[q * 8 + j] += rv[j];
                             }
+                        }
+                        if (f_act == 6) {                    // ReLU after the residual add (Bottleneck tail)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                         }
                     }
                     const uint32_t rowp = sa_out;
@@ -809,6 +814,10 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += rv[j];
                         }
+                        if (p.act == 6) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
                     }
                     if (p.d_fp32) {
                         float* dp = reinterpret_cast<float*>(p.D) + d_off + n;
@@ -928,6 +937,7 @@ __global__ void __launch_bounds__(256) dfu_ref_gemm_kernel(const RefParams p) {
     if (p.res) {
         const float rv = __bfloat162float(p.res[z1 * p.sr1 + z0 * p.sr0 + (long long)m * p.ldr + n]);
         if (p.act == 3) v *= gelu_erf_grad(rv); else if (p.act == 5) v *= rv; else v += rv;
+        if (p.act == 6) v = fmaxf(v, 0.f);
     }
     if (p.d_fp32) {
         float* d = reinterpret_cast<float*>(p.D) + d_off;
@@ -1067,6 +1077,7 @@ cudaError_t set_smem_attrs() {
     DFU_SET_ATTR(false, 6, 1); DFU_SET_ATTR(false, 6, 2); DFU_SET_ATTR(true, 6, 1); DFU_SET_ATTR(true, 6, 2);
     DFU_SET_ATTR(false, 7, 1); DFU_SET_ATTR(false, 7, 2);
     DFU_SET_ATTR(false, 8, 1); DFU_SET_ATTR(false, 8, 2);
+    DFU_SET_ATTR(false, 9, 1); DFU_SET_ATTR(false, 9, 2); DFU_SET_ATTR(false, 10, 1); DFU_SET_ATTR(false, 10, 2);
 #undef DFU_SET_ATTR
     return e;
 }
@@ -1090,6 +1101,8 @@ int pick_epilogue_mode(const GemmParams& p) {
     if (!bias && res && !aux && p.act == 5) return 6;
     if (bias && !res && aux && p.act == 4) return 7;
     if (!bias && res && !aux && p.act == 0) return 8;      // D = AB + res: the skip gradient joins in the dgrad epilogue
+    if (bias && !res && !aux && p.act == 1) return 9;      // eval-mode conv + folded BatchNorm + ReLU
+    if (bias && res && !aux && p.act == 6) return 10;      // ... + identity, ReLU after the add
     return 0;
 }
 
@@ -1124,6 +1137,8 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
             case -6: launch_pair<6, true>(grid, stream, ma, mb, md, mx, p); return;
             case 7: launch_pair<7>(grid, stream, ma, mb, md, mx, p); return;
             case 8: launch_pair<8>(grid, stream, ma, mb, md, mx, p); return;
+            case 9: launch_pair<9>(grid, stream, ma, mb, md, mx, p); return;
+            case 10: launch_pair<10>(grid, stream, ma, mb, md, mx, p); return;
             default: launch_pair<5>(grid, stream, ma, mb, md, mx, p); return;
         }
     }
@@ -1139,6 +1154,8 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
         case -6: dfu_tc_gemm_kernel<true, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 7: dfu_tc_gemm_kernel<false, 7, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         case 8: dfu_tc_gemm_kernel<false, 8, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 9: dfu_tc_gemm_kernel<false, 9, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case 10: dfu_tc_gemm_kernel<false, 10, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
         default: dfu_tc_gemm_kernel<false, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
     }
 }
@@ -1154,8 +1171,8 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
     DFU_CHECK_ARG(!(a->accumulate && a->d_dtype != 1), "dfu_gemm: accumulate needs fp32 output");
     DFU_CHECK_ARG(!(a->accumulate && (a->aux || a->act || a->res || a->bias || a->colstats)),
                   "dfu_gemm: accumulate mode takes no bias/act/res/aux/colstats");
-    DFU_CHECK_ARG(a->act >= 0 && a->act <= 5 && !((a->act == 3 || a->act == 5) && !a->res) && !(a->act == 4 && !a->aux),
-                  "dfu_gemm: act=%d (3 and 5 need res, 4 needs aux)", a->act);
+    DFU_CHECK_ARG(a->act >= 0 && a->act <= 6 && !((a->act == 3 || a->act == 5 || a->act == 6) && !a->res) && !(a->act == 4 && !a->aux),
+                  "dfu_gemm: act=%d (3, 5 and 6 need res, 4 needs aux)", a->act);
     DFU_CHECK_ARG(!a->colstats || (a->colstats_mode >= 1 && a->colstats_mode <= 2 && (long long)a->N * a->colstats_mode <= 4096 &&
                                    a->nb0 * a->nb1 == 1 && a->d_dtype == 0),
                   "dfu_gemm: colstats needs mode 1|2, N x mode <= 4096, a bf16 output and no batching");
@@ -1366,6 +1383,12 @@ int conv_gemm_launch(const dfu_conv_args* a, cudaStream_t stream, int ph, int pw
         DFU_CHECK_ARG(a->mode == 1 && a->Cout <= 2048, "dfu_conv_gemm: colstats is a forward-mode feature (Cout <= 2048)");
         p.colstats = a->colstats;
         p.colstats_mode = 2;
+    }
+    if (a->bias || a->act) {
+        DFU_CHECK_ARG(a->mode == 1 && (a->act == 0 || a->act == 1) && !a->colstats,
+                      "dfu_conv_gemm: bias / ReLU belong to the forward mode (act 0|1) and exclude colstats");
+        p.bias = a->bias;
+        p.act = a->act;
     }
     p.cv_S = a->S;
     p.cv_pad = a->pad;

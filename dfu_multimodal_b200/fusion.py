@@ -4,8 +4,9 @@ Canonical layout = the reference's eval-side model (notebooks/extended_metrics.p
     resnet (ResNet50, fc=Identity) -> 2048  ++  vit (ViT-B/16, num_classes=0) -> 768
     fusion.classifier = Linear(2816,512) -> ReLU -> Dropout -> Linear(512,2)
 `head_layers=3` builds the training script's 2816->512->256->2 head (train_multimodal_fusion.py:305-313).
-forward(rgb, thermal) accepts the reference contract (fp32 NCHW, already normalised) or raw uint8 NHWC batches,
-which are normalised on the device by the a9 kernels (ImageNet mean/std for RGB, 0.5/0.5 for thermal)."""
+forward(rgb, thermal) accepts the reference contract (fp32 NCHW, already normalised) or raw uint8 NHWC batches of any
+size, which are resized to 224x224 (bit-identical to the reference's Resize) and normalised on the device by the a9
+kernels (ImageNet mean/std for RGB, 0.5/0.5 for thermal)."""
 import torch
 import torch.nn as nn
 
@@ -17,13 +18,18 @@ from .vit import DfuVisionTransformer
 
 
 def _prep_rgb(x):
+    """uint8 NHWC images of any size: Resize((224,224)) (Pillow-exact, only when the size differs) + ToTensor + Normalize."""
     if x.dtype == torch.uint8:
+        if tuple(x.shape[1:3]) != (224, 224):
+            return ops.resize_u8(x, (224, 224), "nhwc", "imagenet")
         return ops.preprocess_u8_nhwc(x, "imagenet")
     return x
 
 
 def _prep_thermal(x):
     if x.dtype == torch.uint8:
+        if tuple(x.shape[1:3]) != (224, 224):
+            return ops.resize_u8(x, (224, 224), "patches", "half")
         return ops.preprocess_u8_patches(x, "half")
     return x
 

@@ -69,6 +69,14 @@ class DfuBatchNorm2d(nn.Module):
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self._fold_epoch = 0
+
+    def train(self, mode=True):
+        # the train-mode kernels update the running statistics through raw pointers: whatever was folded from them
+        # (resnet._folded) is stale once this module has been in train() again
+        if mode:
+            self._fold_epoch += 1
+        return super().train(mode)
 
     def forward(self, x, res=None, relu=False):
         return Fn.BatchNormActFn.apply(to_act(x), self.weight, self.bias, res, self.running_mean, self.running_var,

@@ -243,13 +243,14 @@ def conv_implicit_ok(C, Cout, R, S, stride):
 
 
 def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=None, ldo=0, accumulate=False, colstats=None,
-               stride=1):
+               stride=1, bias=None, act=0):
     a = ConvArgs()
     a.mode, a.B, a.H, a.W, a.C = mode, B, H, W, C
     a.Cout, a.R, a.S, a.stride, a.pad = Cout, R, S, stride, pad
     a.x, a.w, a.ldw, a.dy = _p(x), _p(w), (w.stride(0) if w is not None else 0), _p(dy)
     a.out, a.ldo, a.accumulate, a.max_ctas = _p(out), ldo, 1 if accumulate else 0, 0
     a.colstats = _p(colstats)
+    a.bias, a.act = _p(bias), act
     st = _st()
     if GEMM_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,15 +264,16 @@ def _conv_call(mode, B, H, W, C, Cout, R, S, pad, x=None, w=None, dy=None, out=N
     return out
 
 
-def conv_forward(x_nhwc, wm, R, S, pad, colstats=None, stride=1):
-    """y [B,Ho,Wo,Cout] = conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)), stride 1 or 2.
-    colstats ([2*Cout] fp32, zeroed) += per-channel sum / sum of squares of y (BatchNorm batch statistics)."""
+def conv_forward(x_nhwc, wm, R, S, pad, colstats=None, stride=1, bias=None, act=0):
+    """y [B,Ho,Wo,Cout] = act(conv(x [B,H,W,C], wm [Cout, >= R*S*C] bf16, columns ordered (r,s,c)) + bias), stride 1 or 2.
+    colstats ([2*Cout] fp32, zeroed) += per-channel sum / sum of squares of y (BatchNorm batch statistics).
+    bias ([Cout] fp32) / act (0 none, 1 ReLU): the eval-mode BatchNorm folded into the convolution."""
     _need_cuda(x_nhwc, wm)
     B, H, W, C = x_nhwc.shape
     Cout = wm.shape[0]
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     y = torch.empty((B, Ho, Wo, Cout), dtype=BF16, device=x_nhwc.device)
-    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats, stride=stride)
+    return _conv_call(1, B, H, W, C, Cout, R, S, pad, x=x_nhwc, w=wm, out=y, colstats=colstats, stride=stride, bias=bias, act=act)
 
 
 def conv_dgrad(dy_nhwc, wm, H, W, C, R, S, pad, stride=1):
@@ -329,6 +331,32 @@ def preprocess_u8_patches(img_u8, kind="half"):
     check(_L().dfu_preprocess_u8_patches(_p(img_u8), _p(out), B, mean, std, _st()), "preprocess_u8_patches")
     _count()
     return out
+
+
+def resize_u8(img_u8, out_hw=(224, 224), mode="u8", kind="imagenet"):
+    """transforms.Resize(out_hw) of a uint8 [B,Hs,Ws,3] batch, bit-identical to torchvision / Pillow BILINEAR (a9).
+    mode "u8": the resized uint8 images [B,OH,OW,3]; "nhwc": + ToTensor + Normalize(kind) as bf16 (logical (B,3,OH,OW), NHWC
+    memory); "patches": + Normalize + ViT patch unfold -> bf16 [B*196, 768]."""
+    _need_cuda(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[-1] == 3 and img_u8.is_contiguous()
+    B, Hs, Ws, _ = img_u8.shape
+    OH, OW = out_hw
+    L = _L()
+    n_ws = L.dfu_resize_workspace_ints(Hs, Ws, OH, OW)
+    if n_ws <= 0:
+        raise RuntimeError("dfu_resize_workspace_ints: bad sizes %s -> %s" % ((Hs, Ws), (OH, OW)))
+    ws = torch.empty(n_ws, dtype=torch.int32, device=img_u8.device)
+    code = {"u8": 0, "nhwc": 1, "patches": 2}[mode]
+    if code == 0:
+        out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=img_u8.device)
+        mean = std = None
+    else:
+        out = (torch.empty((B, OH, OW, 3), dtype=BF16, device=img_u8.device) if code == 1 else
+               torch.empty((B * 196, 768), dtype=BF16, device=img_u8.device))
+        mean, std = _norm_consts(kind)
+    check(L.dfu_resize_u8(_p(img_u8), Hs * Ws * 3, B, Hs, Ws, OH, OW, code, _p(out), _p(ws), mean, std, _st()), "resize_u8")
+    _count(3)
+    return out.permute(0, 3, 1, 2) if code == 1 else out
 
 
 def nchw_f32_to_nhwc_bf16(x):
@@ -400,6 +428,28 @@ def col2im(dcol, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc):
 
 
 # ------------------------------------------------------------------------------------------ BatchNorm
+# bumped by FusedAdamW.step(): parameters change through raw pointers there, without touching torch's version counters
+PARAM_EPOCH = [0]
+
+
+def fold_bn_weights(weight, gamma, beta, running_mean, running_var, eps, out=None):
+    """Eval-mode BatchNorm folded into the convolution weights: (bf16 [Cout, round8(K)] with rows w * gamma/sqrt(var+eps),
+    fp32 bias [Cout] = beta - mean * gamma/sqrt(var+eps)).  `weight` is a (Cout,Cin,R,S) parameter stored channels_last."""
+    _need_cuda(weight, gamma, beta, running_mean, running_var)
+    Cout = weight.shape[0]
+    K = weight.numel() // Cout
+    ldo = (K + 7) // 8 * 8
+    if out is not None and out[0].shape == (Cout, ldo) and out[0].device == weight.device:
+        wf, bias = out                  # refreshed in place: captured CUDA graphs keep reading the same buffers
+    else:
+        wf = torch.empty((Cout, ldo), dtype=BF16, device=weight.device)
+        bias = torch.empty(Cout, dtype=F32, device=weight.device)
+    check(_L().dfu_fold_bn_weights(_p(weight), Cout, K, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, _p(wf), ldo,
+                                   _p(bias), _st()), "fold_bn_weights")
+    _count()
+    return wf, bias
+
+
 def bn_forward(y2d, gamma, beta, running_mean, running_var, nbt, res2d, relu, training, eps, momentum, sums=None,
                want_mask=False):
     """`sums` ([2C] fp32: per-channel sum and sum of squares of y) may come from the convolution GEMM's epilogue.

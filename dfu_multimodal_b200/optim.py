@@ -142,6 +142,7 @@ class FusedAdamW(torch.optim.Optimizer):
         L = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         ticked = set()         # the shared counter advances once per step() however many groups read it
+        ops.PARAM_EPOCH[0] += 1        # parameters change below without torch's version counters noticing (folded-BN caches)
         for gi, group in enumerate(self.param_groups):
             params, grads = [], []
             g_bf16, scale = False, 1.0

@@ -2,10 +2,13 @@
 Module/parameter names equal torchvision's so `resnet.*` / `rgb_branch.*` / `backbone.*` checkpoints load
 (SURVEY.md 8b).  Reference constructor: torch.hub.load('pytorch/vision:v0.13.1','resnet50')
 (notebooks/train_multimodal_fusion.py:294)."""
+import os
+
 import torch
 import torch.nn as nn
 
 from . import functional as Fn
+from . import ops
 from .nn import (DfuAvgPoolFlatten, DfuBatchNorm2d, DfuConv2d, DfuLinear, DfuMaxPool2d, DfuReLU, convert_head,
                  has_hooks, to_act)
 
@@ -15,11 +18,69 @@ def _bn(y, bn, relu, res=None, sums=None):
                                    bn.num_batches_tracked, relu, bn.training, bn.eps, bn.momentum, sums)
 
 
+# eval()-mode inference folds every BatchNorm into the convolution that feeds it (DFU_FOLD_BN=0: separate bn_apply pass)
+FOLD_BN = os.environ.get("DFU_FOLD_BN", "1") == "1"
+
+
+def _folded(conv, bn):
+    """(bf16 weights scaled by gamma/sqrt(var+eps), fp32 bias beta - mean*gamma/sqrt(var+eps)) of a conv -> eval-BatchNorm
+    pair, cached on the conv and recomputed IN PLACE when anything it was computed from may have changed: torch-visible
+    edits (version counters), a train() phase of the BatchNorm, a FusedAdamW step."""
+    key = (conv.weight._version, conv.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, bn.running_mean.data_ptr(), bn._fold_epoch, ops.PARAM_EPOCH[0])
+    cached = conv.__dict__.get("_dfu_folded")
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    if not conv.weight.permute(0, 2, 3, 1).is_contiguous():
+        raise RuntimeError("conv weights must be stored channels_last (Cout,R,S,Cin); use DfuConv2d parameters")
+    wf, bias = ops.fold_bn_weights(conv.weight.detach(), bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                   bn.eps, out=(cached[1], cached[2]) if cached is not None else None)
+    conv.__dict__["_dfu_folded"] = (key, wf, bias)
+    return wf, bias
+
+
+def refresh_folded(module):
+    """Brings every folded conv/BatchNorm pair under `module` up to date (in place).  train.EvalStep calls it before
+    replaying a captured graph, whose kernels read the folded buffers but do not contain the folding itself."""
+    if not FOLD_BN:
+        return
+    for m in module.modules():
+        if isinstance(m, DfuBottleneck):
+            _folded(m.conv1, m.bn1), _folded(m.conv2, m.bn2), _folded(m.conv3, m.bn3)
+            if m.downsample is not None:
+                _folded(m.downsample[0], m.downsample[1])
+        elif isinstance(m, DfuResNet50):
+            _folded(m.conv1, m.bn1)
+
+
+def _conv_bn_folded(x, conv, bn, relu, res=None):
+    """Inference: act(conv(x, W * s) + b [+ res]) in ONE GEMM launch -- scale, shift, residual and ReLU ride in the epilogue
+    (torchvision Bottleneck in eval(): conv -> bn -> relu / conv3 -> bn3 -> += identity -> relu)."""
+    xn = ops.as_nhwc(x)
+    B, H, W, C = xn.shape
+    Cout, _, R, S = conv.weight.shape
+    stride, pad = conv.stride[0], conv.padding[0]
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    wf, bias = _folded(conv, bn)
+    res2 = ops.as_nhwc(res).reshape(B * Ho * Wo, Cout) if res is not None else None
+    act = (6 if res2 is not None else 1) if relu else 0
+    if R == 1 and S == 1 and stride == 1 and pad == 0:
+        y, _ = ops.linear_forward(xn.reshape(B * H * W, C), wf, bias, act=act, res=res2)
+    elif ops.conv_implicit_ok(C, Cout, R, S, stride) and res2 is None:
+        y = ops.conv_forward(xn, wf, R, S, pad, stride=stride, bias=bias, act=act)
+    else:                                    # the 3-channel stem: explicit patch matrix
+        y, _ = ops.linear_forward(ops.im2col(xn, R, S, stride, pad, Ho, Wo, wf.shape[1]), wf, bias, act=act, res=res2)
+    return y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+
+
 def _conv_bn(x, conv, bn, relu, res=None):
-    """conv -> BatchNorm (+res) (+ReLU); in train() the batch statistics come out of the conv GEMM's epilogue."""
+    """conv -> BatchNorm (+res) (+ReLU).  train(): the batch statistics come out of the conv GEMM's epilogue; eval() without
+    autograd: BatchNorm is folded into the convolution (one launch); eval() under autograd (Grad-CAM): separate kernels."""
     if bn.training:
         y, sums = Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0], False, True)
         return _bn(y, bn, relu, res, sums)
+    if FOLD_BN and not torch.is_grad_enabled():
+        return _conv_bn_folded(x, conv, bn, relu, res)
     return _bn(Fn.Conv2dFn.apply(x, conv.weight, conv.stride[0], conv.padding[0]), bn, relu, res)
 
 

@@ -7,6 +7,7 @@ import torch
 
 from . import ops
 from .functional import cross_entropy
+from .resnet import refresh_folded
 
 
 class TrainStep:
@@ -115,6 +116,7 @@ class EvalStep:
         self.model.eval()
         if any(t.shape[0] != inputs[0].shape[0] for t in inputs):
             raise RuntimeError("EvalStep: batch sizes differ: %s" % ([int(t.shape[0]) for t in inputs],))
+        refresh_folded(self.model)       # folded conv/BatchNorm weights are inputs of the captured graphs, not part of them
         key = TrainStep._key(*inputs)
         entry = self.graphs.get(key) if self.use_graph else None
         if entry is None:

@@ -41,7 +41,8 @@ int dfu_set_sm_budget(int32_t n_sms);
  *   z = z1*nb0 + z0, element strides s?0 / s?1 per batch dim.  All strides in ELEMENTS.
  *   d_dtype: 0 = bf16, 1 = fp32.  accumulate=1 (fp32 only): D += result (atomic, enables split-K).
  *   aux (bf16, same geometry as D) receives the pre-activation value when non-null.
- *   act: 0 none, 1 relu, 2 gelu(erf), 3 = D = (alpha*acc + bias) * gelu'(res) (res holds the pre-activation; fuses the
+ *   act: 0 none, 1 relu, 6 = relu(alpha*acc + bias + res) (ReLU AFTER the residual add: torchvision Bottleneck tail with the
+ *   eval-mode BatchNorm folded into weights and bias), 2 gelu(erf), 3 = D = (alpha*acc + bias) * gelu'(res) (res holds the pre-activation; fuses the
  *   GELU backward into the dgrad GEMM); 4 = gelu(erf) with aux receiving gelu'(pre-activation) instead of the
  *   pre-activation (aux required); 5 = D = (alpha*acc + bias) * res (res = the derivative stored by a forward act=4).
  *   impl: 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT fp32 check kernel.
@@ -92,8 +93,17 @@ typedef struct {
     int32_t accumulate;
     int32_t max_ctas;
     float* colstats;   /* mode 1 only, may be null: [2*Cout] fp32 (caller zeroes) += per-channel sum and sum of squares of y */
+    const float* bias; /* mode 1 only, may be null: y = act(conv + bias[Cout]) -- eval-mode BatchNorm folded into the convolution */
+    int32_t act;       /* mode 1 only: 0 none, 1 ReLU */
 } dfu_conv_args;
 int dfu_conv_gemm(const dfu_conv_args* a, void* stream);
+
+/* Eval-mode BatchNorm folded into the convolution that feeds it (extended_metrics.py:630-640 runs the model in eval()):
+ * w_out[co, k] = bf16(w[co, k] * gamma[co] / sqrt(var[co] + eps)) (row stride ldo >= K, padding zeroed),
+ * bias_out[co] = beta[co] - mean[co] * gamma[co] / sqrt(var[co] + eps).  Replaces aten::native_batch_norm(training=False)
+ * after aten::convolution by one GEMM epilogue (dfu_gemm bias/act 1|6, dfu_conv_gemm bias/act). */
+int dfu_fold_bn_weights(const float* w, int32_t Cout, int32_t K, const float* gamma, const float* beta, const float* mean,
+                        const float* var, float eps, void* w_out, int64_t ldo, float* bias_out, void* stream);
 
 /* ------------------------------- layout / preprocessing ------------------------------------ */
 /* a9: ToTensor+Normalize (train_multimodal_fusion.py:184-188,201-205) on uint8 HWC images.
@@ -245,6 +255,62 @@ int dfu_gradcam(const void* A, int32_t CA, const void* G, int32_t CG, int32_t HW
 int dfu_saliency(const float* dimg, float* out, float* max_scratch, int32_t C, int32_t HW, void* stream);
 /* TTA vote: probs [n, V] -> mean prob and majority vote (mean(p>0.5) > 0.5). */
 int dfu_tta_vote(const float* probs, float* mean_prob, int64_t* pred, int32_t n, int32_t V, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9, resize half: transforms.Resize((224,224)) of the reference pipelines (train_multimodal_fusion.py:174,186,195,204;
+ * extended_metrics.py:290-300) fused with ToTensor + Normalize.  Replaces torchvision F.resize -> PIL.Image.resize(BILINEAR)
+ * (Pillow ImagingResample: antialiased triangle filter, 22-bit fixed-point coefficients, horizontal then vertical pass, each
+ * rounded to uint8) and is BIT-IDENTICAL to it; out_mode 0 returns the resized uint8 image itself.
+ *   src: B uint8 HWC images of one size [Hs, Ws, 3], image b at src + b * img_stride_bytes.
+ *   out_mode 0: uint8 [B, OH, OW, 3];  1: normalised bf16 NHWC [B, OH, OW, 3];  2: normalised bf16 ViT patch matrix
+ *   [B*196, 768] (OH = OW = 224).  workspace: dfu_resize_workspace_ints(Hs, Ws, OH, OW) int32 values (coefficient tables,
+ *   written by the call).  mean3/std3 are HOST pointers (unused for mode 0).
+ * ------------------------------------------------------------------------------------------- */
+int dfu_resize_workspace_ints(int32_t Hs, int32_t Ws, int32_t OH, int32_t OW);
+int dfu_resize_u8(const uint8_t* src, int64_t img_stride_bytes, int32_t B, int32_t Hs, int32_t Ws, int32_t OH, int32_t OW,
+                  int32_t out_mode, void* out, int32_t* workspace, const float* mean3_host, const float* std3_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 VALIDATION MODE (north_star: logits within 1e-4 of the fp32 reference "in fp32-accum validation mode").
+ * The inference path once more with fp32 activations (NHWC rows / token rows), the fp32 master weights and fp32
+ * accumulation (fp64 for statistics), as plain SIMT kernels; dfu_multimodal_b200/validation.py drives them.  Each entry
+ * replaces the same ATen call as its bf16 sibling above (aten::convolution via im2col + mm, aten::native_batch_norm,
+ * aten::max_pool2d, aten::mean, aten::native_layer_norm, aten::_softmax, aten::addmm / bmm, aten::gelu, aten::cat).
+ * dfu_v32_gemm: D[z][m][n] = act(alpha * sum_k A[z][m][k] * B[z][n][k] + bias[n]) + res[z][m][n], A and B addressed
+ * by element strides (row stride, column stride, two batch strides), act 0 none / 1 relu / 2 gelu(erf).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t M, N, K, nb0, nb1;
+    const float* A; int64_t a_row_stride, a_col_stride, sa0, sa1;
+    const float* B; int64_t b_row_stride, b_col_stride, sb0, sb1;
+    float* D; int64_t ldd, sd0, sd1;
+    const float* bias;
+    const float* res; int64_t ldr, sr0, sr1;
+    float alpha;
+    int32_t act;
+} dfu_v32_gemm_args;
+int dfu_v32_gemm(const dfu_v32_gemm_args* a, void* stream);
+/* uint8 NHWC -> fp32 NHWC, (x/255 - mean)/std; mean3/std3 are HOST pointers to 3 floats. */
+int dfu_v32_preprocess_u8(const uint8_t* img_nhwc, float* out_nhwc, int64_t npix, const float* mean3_host, const float* std3_host, void* stream);
+int dfu_v32_nchw_to_nhwc(const float* x, float* y, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* col[(b,ho,wo), (r,s,c)] of an NHWC tensor, zero padded. */
+int dfu_v32_im2col(const float* x, float* col, int32_t B, int32_t H, int32_t W, int32_t C, int32_t R, int32_t S, int32_t stride,
+                   int32_t pad, int32_t Ho, int32_t Wo, void* stream);
+/* timm PatchEmbed unfold of fp32 NHWC [B,224,224,3] -> [B*196, 768], columns ordered (c,i,j). */
+int dfu_v32_patchify(const float* x_nhwc, float* out, int32_t B, void* stream);
+int dfu_v32_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream);
+int dfu_v32_vit_assemble(const float* patch_out, const float* cls, const float* pos, float* tokens, int32_t B, int32_t T, int32_t D,
+                         void* stream);
+/* per-channel batch mean / biased variance of y [M, C] (train-mode BatchNorm), fp64 accumulation. */
+int dfu_v32_bn_batch_stats(const float* y, float* mean, float* var, int64_t M, int32_t C, void* stream);
+/* out = [relu]((y - mean)/sqrt(var + eps) * gamma + beta [+ res]). */
+int dfu_v32_bn_apply(const float* y, const float* mean, const float* var, const float* gamma, const float* beta, const float* res,
+                     float* out, int64_t M, int32_t C, int32_t relu, float eps, void* stream);
+int dfu_v32_maxpool3x3s2(const float* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int dfu_v32_avgpool(const float* x, float* y, int32_t B, int32_t HW, int32_t C, void* stream);
+int dfu_v32_layernorm(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int32_t D, float eps, void* stream);
+/* in place over rows of length T with row stride ld. */
+int dfu_v32_softmax_rows(float* x, int64_t rows, int32_t T, int64_t ld, void* stream);
 
 #ifdef __cplusplus
 }

@@ -178,10 +178,12 @@ class OracleThermalOnly(nn.Module):
         return self.vit(x)
 
 
-def seeded_init_(model, seed=0, calibrate=True):
+def seeded_init_(model, seed=0, calibrate=True, bn3_gamma=0.25):
     """Deterministic init shared by oracle and CUDA path through one state_dict: conv kaiming-normal
     fan_out, BN gamma=1 beta=0, linear / ViT weights N(0, 0.02), zero bias, pos_embed / cls N(0, 0.02).
-    BN running stats are then calibrated on one seeded batch (calibrate_bn_) so eval mode is well scaled."""
+    BN running stats are then calibrated on one seeded batch (calibrate_bn_) so eval mode is well scaled.
+    bn3_gamma: weight of the last BatchNorm of each Bottleneck -- 0.25 by default (see below); 1.0 gives SURVEY 8(d)'s plain
+    gamma=1 initialisation, which the fp32 validation-mode tests use."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in model.named_parameters():
@@ -195,7 +197,7 @@ def seeded_init_(model, seed=0, calibrate=True):
                 # gamma=1 everywhere amplifies ANY rounding perturbation ~1.25x per block (measured: bf16 rounding
                 # at block boundaries alone gives 17% error at layer4); 0.25 keeps the synthetic network as
                 # well-conditioned as a trained one, so parity tests measure the kernels rather than chaos.
-                p.fill_(0.25 if name.endswith("bn3.weight") else 1.0)
+                p.fill_(bn3_gamma if name.endswith("bn3.weight") else 1.0)
             else:
                 p.copy_(torch.randn(p.shape, generator=g) * 0.02)
         for name, b in model.named_buffers():

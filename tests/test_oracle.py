@@ -87,3 +87,20 @@ def test_seeded_init_is_deterministic():
     a = R.seeded_init_(R.OracleThermalOnly(), 5).state_dict()
     b = R.seeded_init_(R.OracleThermalOnly(), 5).state_dict()
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_resize_restatement_is_bit_identical_to_pillow():
+    """oracle/resize_pil.py (numpy restatement of Pillow's ImagingResample) against the library the reference really calls:
+    torchvision.transforms.Resize((224,224)) on a PIL image (train_multimodal_fusion.py:186)."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from oracle.resize_pil import precompute_coeffs, resize_bilinear_u8
+    rng = np.random.RandomState(0)
+    tf = transforms.Resize((224, 224))
+    for h, w in [(224, 224), (240, 200), (300, 260), (180, 232), (480, 640), (100, 90), (225, 223), (448, 448), (37, 1024), (1, 1)]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ref = np.asarray(tf(Image.fromarray(img)))
+        assert np.array_equal(resize_bilinear_u8(img), ref), (h, w)
+    b, c, k = precompute_coeffs(448, 224)
+    assert k == 5 and int(c.sum(1).min()) >= (1 << 22) - 4 and int(c.sum(1).max()) <= (1 << 22) + 4
