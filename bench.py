@@ -650,7 +650,7 @@ def main():
     bucketer = None
     if world > 1:
         bucketer = GradBucketer(list(model.parameters()))
-        opt.set_grad_source(bucketer.grad_source)
+        opt.set_grad_source(bucketer.grad_source, bucketer)
     # synthetic data: 2 distinct batches alternate so no step re-reads the previous step's inputs from L2
     host = []
     for s in range(2):

@@ -58,7 +58,7 @@ class AdamWTensor(ctypes.Structure):
 
 
 _SCALARS = {
-    "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float,
+    "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float, "double": ctypes.c_double,
     "int": ctypes.c_int,
 }
 

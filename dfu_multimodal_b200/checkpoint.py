@@ -83,3 +83,21 @@ def save_checkpoint(path, model, optimizer, epoch, val_f1, history):
     torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
                 "optimizer_state_dict": optimizer.state_dict() if optimizer is not None else None,
                 "val_f1": val_f1, "history": history}, path)
+
+
+def resume(path_or_ckpt, model, optimizer=None, target="fusion", map_location="cpu"):
+    """Continue a run from a checkpoint in the reference's container (train_multimodal_fusion.py:433-439; the reference saves
+    `optimizer_state_dict` but never reloads it).  The model weights load through the key remap (any scheme); the optimizer
+    state loads into FusedAdamW or a stock torch.optim.AdamW alike -- parameter order is the modules' registration order
+    (RGB branch, thermal branch, head), which all schemes share.  Returns {'epoch', 'val_f1', 'history'}."""
+    ckpt = torch.load(path_or_ckpt, map_location=map_location, weights_only=False) if isinstance(path_or_ckpt, (str, bytes)) or hasattr(
+        path_or_ckpt, "__fspath__") else path_or_ckpt
+    load_into(model, ckpt, target=target, strict=True)
+    osd = ckpt.get("optimizer_state_dict")
+    if optimizer is not None and osd:
+        n_ckpt = sum(len(g["params"]) for g in osd["param_groups"])
+        n_here = sum(len(g["params"]) for g in optimizer.param_groups)
+        if n_ckpt != n_here:
+            raise RuntimeError("optimizer state holds %d parameters, the optimizer %d (different head depth?)" % (n_ckpt, n_here))
+        optimizer.load_state_dict(osd)
+    return {"epoch": ckpt.get("epoch", 0), "val_f1": ckpt.get("val_f1"), "history": ckpt.get("history")}

@@ -3,6 +3,7 @@
 #include "../../include/dfu_b200.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -37,6 +38,11 @@ int dfu_num_sms() {
 extern "C" int dfu_set_sm_budget(int32_t n_sms) {
     g_sm_budget = n_sms > 0 ? n_sms : 0;
     return DFU_OK;
+}
+
+bool dfu_pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("DFU_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 extern "C" const char* dfu_last_error(void) { return g_err; }

@@ -50,6 +50,7 @@ constexpr int FWD_SMEM = F_END + 1024;
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int H, float scale) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t qk_full, qk_empty, v_full, v_empty, s_full[2], p_full[2], o_full[2], o_empty[2];
     __shared__ uint32_t tmem_slot;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
                 bf16* __restrict__ dqkv, int B, int T, int H, float scale) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ops_full, ops_empty, st_full, tile_full, tile_free, acc_full, acc_empty, dq_full, dq_empty;
     __shared__ uint32_t tmem_slot;
@@ -498,6 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                      const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
                      bf16* __restrict__ dqkv, int B, int T, int H, float scale) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
     __shared__ uint64_t d_full[2], d_empty[2];
@@ -793,7 +796,7 @@ extern "C" int dfu_attention_fwd(const void* qkv, void* out, float* lse, int32_t
     }
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
-    attn_fwd_kernel<<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, (bf16*)out, lse, B, T, H, scale);
+    dfu_launch(attn_fwd_kernel, grid, THREADS, FWD_SMEM, (cudaStream_t)stream, map_q, map_kv, (bf16*)out, lse, B, T, H, scale);
     DFU_CHECK_LAUNCH("attn_fwd_kernel");
     return DFU_OK;
 }
@@ -823,10 +826,10 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
     if (g_bwd_pipe)
-        attn_bwd_pipe_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(map_qkv, map_do, (const bf16*)out,
+        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out,
                                                                                 (const bf16*)dout, lse, (bf16*)dqkv, B, T, H, scale);
     else
-        attn_bwd_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
+        dfu_launch(attn_bwd_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
                                                                            lse, (bf16*)dqkv, B, T, H, scale);
     DFU_CHECK_LAUNCH("attn_bwd_kernel");
     return DFU_OK;

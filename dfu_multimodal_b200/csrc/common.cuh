@@ -34,7 +34,40 @@ static inline int dfu_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 // Number of SMs of the current device (cached).
 int dfu_num_sms();
 
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched through dfu_launch(), i.e. with
+// cudaLaunchAttributeProgrammaticStreamSerialization, and begins with pdl_sync(): `griddepcontrol.launch_dependents` lets
+// the NEXT kernel of the stream be scheduled as soon as all CTAs of this one are resident (its CTAs take over SMs as this
+// kernel's tail drains and run their prologue), `griddepcontrol.wait` blocks until the PREVIOUS kernel has completed and
+// its writes are visible.  Every kernel waits before its first global-memory access, so the chain of waits keeps the
+// stream's order for data (a kernel that passed its wait implies all earlier kernels have finished).  Saves the launch
+// latency and prologue at each of the ~600 kernel boundaries of a train step (CUDA graphs keep the edges programmatic).
+// DFU_PDL=0 launches without the attribute (the two instructions are then no-ops).
+bool dfu_pdl_enabled();
+
 #ifdef __CUDACC__
+#include <utility>
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t dfu_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = dfu_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;

@@ -23,6 +23,7 @@ struct Norm3 {
 // thread handles 48 bytes (three 16-byte loads) -> 48 bf16 (six 16-byte stores).
 __global__ void __launch_bounds__(256) preprocess_u8_nhwc_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out,
                                                                 long long n_groups, long long n_bytes, Norm3 nm) {
+    pdl_sync();
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_groups;
          g += (long long)gridDim.x * blockDim.x) {
         const long long base = g * 48;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_nhwc_kernel(const uint8_t* 
 // One thread produces 8 consecutive j (one 16-byte store) from 24 input bytes.
 __global__ void __launch_bounds__(256) preprocess_u8_patches_kernel(const uint8_t* __restrict__ in,
                                                                    bf16* __restrict__ out, int B, Norm3 nm) {
+    pdl_sync();
     const long long total = (long long)B * 196 * 96;   // 768/8 = 96 vectors per patch row
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_patches_kernel(const uint8_
 // Tiled transpose through shared memory: [C, HW] <-> [HW, C] per image.
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C,
                                                            int HW) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ out, int C,
                                                            int HW) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restric
 
 // ------------------------------------------------------------------ fp32 NCHW -> ViT patches and adjoint
 __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ in, bf16* __restrict__ out, int B) {
+    pdl_sync();
     const long long total = (long long)B * 196 * 96;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) unpatchify_f32_kernel(const bf16* __restrict__ dp, float* __restrict__ dimg,
                                                              int B) {
+    pdl_sync();
     const long long total = (long long)B * 196 * 96;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(256) unpatchify_f32_kernel(const bf16* __restr
 __global__ void __launch_bounds__(256) im2col_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int B, int H,
                                                          int W, int C, int R, int S, int stride, int pad, int Ho, int Wo,
                                                          long long ldc) {
+    pdl_sync();
     const int cv = C / 8;
     const long long per_row = (long long)R * S * cv;
     const long long total = (long long)B * Ho * Wo * per_row;
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(256) im2col_vec_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(256) im2col_scalar_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int B,
                                                             int H, int W, int C, int R, int S, int stride, int pad,
                                                             int Ho, int Wo, long long ldc) {
+    pdl_sync();
     const int Kc = R * S * C;
     const long long total = (long long)B * Ho * Wo * ldc;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -214,6 +222,7 @@ constexpr int C3_ROWS_PER_BLOCK = 4;      // output rows per block (their input 
 __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W,
                                                         int R, int S, int stride, int pad, int Ho, int Wo,
                                                         int ldc) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [(C3_ROWS_PER_BLOCK-1)*stride + R][W*3]
     const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(256) im2col_c3_kernel(const bf16* __restrict__
 template <int R, int S, int STRIDE, int PAD, int LDC>
 __global__ void __launch_bounds__(256) im2col_c3_fixed_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W,
                                                               int Ho, int Wo) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     bf16* rows = reinterpret_cast<bf16*>(sm_raw);            // [(C3_ROWS_PER_BLOCK-1)*STRIDE + R][W*3]
     const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(256) im2col_c3_fixed_kernel(const bf16* __rest
 }
 // Zero the pad columns [Kc, ldc) of the vector path when ldc > Kc.
 __global__ void __launch_bounds__(256) zero_pad_cols_kernel(bf16* __restrict__ col, long long rows, int Kc, long long ldc) {
+    pdl_sync();
     const int padw = (int)(ldc - Kc);
     const long long total = rows * padw;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(256) zero_pad_cols_kernel(bf16* __restrict__ c
 __global__ void __launch_bounds__(256) col2im_vec_kernel(const bf16* __restrict__ col, bf16* __restrict__ dx, int B, int H,
                                                          int W, int C, int R, int S, int stride, int pad, int Ho, int Wo,
                                                          long long ldc) {
+    pdl_sync();
     const int cv = C / 8;
     const long long total = (long long)B * H * W * cv;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -382,6 +394,7 @@ __global__ void __launch_bounds__(256) col2im_vec_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(256) col2im_scalar_kernel(const bf16* __restrict__ col, bf16* __restrict__ dx, int B,
                                                             int H, int W, int C, int R, int S, int stride, int pad,
                                                             int Ho, int Wo, long long ldc) {
+    pdl_sync();
     const long long total = (long long)B * H * W * C;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -426,8 +439,7 @@ extern "C" int dfu_preprocess_u8_nhwc(const uint8_t* in, void* out, int64_t n_pi
     DFU_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dfu_preprocess_u8_nhwc: unaligned buffers");
     const long long n_bytes = n_pixels * 3;
     const long long groups = (n_bytes + 47) / 48;
-    preprocess_u8_nhwc_kernel<<<grid_for(groups, 256), 256, 0, (cudaStream_t)stream>>>(
-        in, (bf16*)out, groups, n_bytes, make_norm(mean3_host, std3_host));
+    dfu_launch(preprocess_u8_nhwc_kernel, grid_for(groups, 256), 256, 0, (cudaStream_t)stream, in, (bf16*)out, groups, n_bytes, make_norm(mean3_host, std3_host));
     DFU_CHECK_LAUNCH("preprocess_u8_nhwc");
     return DFU_OK;
 }
@@ -435,8 +447,7 @@ extern "C" int dfu_preprocess_u8_nhwc(const uint8_t* in, void* out, int64_t n_pi
 extern "C" int dfu_preprocess_u8_patches(const uint8_t* in, void* out, int32_t B, const float* mean3_host,
                                          const float* std3_host, void* stream) {
     DFU_CHECK_ARG(in && out && B > 0 && mean3_host && std3_host, "dfu_preprocess_u8_patches: bad args");
-    preprocess_u8_patches_kernel<<<grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream>>>(
-        in, (bf16*)out, B, make_norm(mean3_host, std3_host));
+    dfu_launch(preprocess_u8_patches_kernel, grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream, in, (bf16*)out, B, make_norm(mean3_host, std3_host));
     DFU_CHECK_LAUNCH("preprocess_u8_patches");
     return DFU_OK;
 }
@@ -445,7 +456,7 @@ extern "C" int dfu_nchw_f32_to_nhwc_bf16(const float* in, void* out, int32_t B, 
                                          void* stream) {
     DFU_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "dfu_nchw_f32_to_nhwc_bf16: bad args");
     dim3 grid(dfu_cdiv(H * W, 32), dfu_cdiv(C, 32), B);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, C, H * W);
+    dfu_launch(nchw_to_nhwc_kernel, grid, 256, 0, (cudaStream_t)stream, in, (bf16*)out, C, H * W);
     DFU_CHECK_LAUNCH("nchw_to_nhwc");
     return DFU_OK;
 }
@@ -453,7 +464,7 @@ extern "C" int dfu_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t B, 
                                          void* stream) {
     DFU_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "dfu_nhwc_bf16_to_nchw_f32: bad args");
     dim3 grid(dfu_cdiv(H * W, 32), dfu_cdiv(C, 32), B);
-    nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, out, C, H * W);
+    dfu_launch(nhwc_to_nchw_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)in, out, C, H * W);
     DFU_CHECK_LAUNCH("nhwc_to_nchw");
     return DFU_OK;
 }
@@ -461,13 +472,13 @@ extern "C" int dfu_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t B, 
 extern "C" int dfu_patchify_f32(const float* in, void* out, int32_t B, void* stream) {
     DFU_CHECK_ARG(in && out && B > 0, "dfu_patchify_f32: bad args");
     DFU_CHECK_ARG(((uintptr_t)in & 15) == 0, "dfu_patchify_f32: input must be 16-byte aligned");
-    patchify_f32_kernel<<<grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, B);
+    dfu_launch(patchify_f32_kernel, grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream, in, (bf16*)out, B);
     DFU_CHECK_LAUNCH("patchify_f32");
     return DFU_OK;
 }
 extern "C" int dfu_unpatchify_f32(const void* dpatches, float* dimg, int32_t B, void* stream) {
     DFU_CHECK_ARG(dpatches && dimg && B > 0, "dfu_unpatchify_f32: bad args");
-    unpatchify_f32_kernel<<<grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dpatches,
+    dfu_launch(unpatchify_f32_kernel, grid_for((long long)B * 196 * 96, 256), 256, 0, (cudaStream_t)stream, (const bf16*)dpatches,
                                                                                                   dimg, B);
     DFU_CHECK_LAUNCH("unpatchify_f32");
     return DFU_OK;
@@ -480,27 +491,25 @@ extern "C" int dfu_im2col_nhwc(const void* x, void* col, int32_t B, int32_t H, i
     const long long rows = (long long)B * Ho * Wo;
     if (C % 8 == 0 && ldc % 8 == 0) {
         const long long total = rows * R * S * (C / 8);
-        im2col_vec_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>((const bf16*)x, (bf16*)col, B, H, W, C, R, S, stride,
+        dfu_launch(im2col_vec_kernel, grid_for(total, 256, 16), 256, 0, st, (const bf16*)x, (bf16*)col, B, H, W, C, R, S, stride,
                                                                     pad, Ho, Wo, ldc);
         DFU_CHECK_LAUNCH("im2col_vec");
         if (ldc > (int64_t)R * S * C) {
-            zero_pad_cols_kernel<<<grid_for(rows * (ldc - R * S * C), 256), 256, 0, st>>>((bf16*)col, rows, R * S * C, ldc);
+            dfu_launch(zero_pad_cols_kernel, grid_for(rows * (ldc - R * S * C), 256), 256, 0, st, (bf16*)col, rows, R * S * C, ldc);
             DFU_CHECK_LAUNCH("zero_pad_cols");
         }
     } else if (C == 3 && (W * 3) % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0 &&
                (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16) <= 48 * 1024) {
         const int hblocks = (Ho + C3_ROWS_PER_BLOCK - 1) / C3_ROWS_PER_BLOCK;
         if (R == 7 && S == 7 && stride == 2 && pad == 3 && ldc == 152) {
-            im2col_c3_fixed_kernel<7, 7, 2, 3, 152><<<B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * 2 + 7) * W * 3 * sizeof(bf16), st>>>(
-                (const bf16*)x, (bf16*)col, H, W, Ho, Wo);
+            dfu_launch(im2col_c3_fixed_kernel<7, 7, 2, 3, 152>, B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * 2 + 7) * W * 3 * sizeof(bf16), st, (const bf16*)x, (bf16*)col, H, W, Ho, Wo);
             DFU_CHECK_LAUNCH("im2col_c3_fixed");
             return DFU_OK;
         }
-        im2col_c3_kernel<<<B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16), st>>>(
-            (const bf16*)x, (bf16*)col, H, W, R, S, stride, pad, Ho, Wo, (int)ldc);
+        dfu_launch(im2col_c3_kernel, B * hblocks, 256, (size_t)((C3_ROWS_PER_BLOCK - 1) * stride + R) * W * 3 * sizeof(bf16), st, (const bf16*)x, (bf16*)col, H, W, R, S, stride, pad, Ho, Wo, (int)ldc);
         DFU_CHECK_LAUNCH("im2col_c3");
     } else {
-        im2col_scalar_kernel<<<grid_for(rows * ldc, 256, 16), 256, 0, st>>>((const bf16*)x, (bf16*)col, B, H, W, C, R, S,
+        dfu_launch(im2col_scalar_kernel, grid_for(rows * ldc, 256, 16), 256, 0, st, (const bf16*)x, (bf16*)col, B, H, W, C, R, S,
                                                                             stride, pad, Ho, Wo, ldc);
         DFU_CHECK_LAUNCH("im2col_scalar");
     }
@@ -512,12 +521,10 @@ extern "C" int dfu_col2im_nhwc(const void* col, void* dx, int32_t B, int32_t H, 
     DFU_CHECK_ARG(col && dx && B > 0 && ldc >= (int64_t)R * S * C, "dfu_col2im_nhwc: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     if (C % 8 == 0 && ldc % 8 == 0) {
-        col2im_vec_kernel<<<grid_for((long long)B * H * W * (C / 8), 256, 16), 256, 0, st>>>(
-            (const bf16*)col, (bf16*)dx, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc);
+        dfu_launch(col2im_vec_kernel, grid_for((long long)B * H * W * (C / 8), 256, 16), 256, 0, st, (const bf16*)col, (bf16*)dx, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc);
         DFU_CHECK_LAUNCH("col2im_vec");
     } else {
-        col2im_scalar_kernel<<<grid_for((long long)B * H * W * C, 256, 16), 256, 0, st>>>(
-            (const bf16*)col, (bf16*)dx, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc);
+        dfu_launch(col2im_scalar_kernel, grid_for((long long)B * H * W * C, 256, 16), 256, 0, st, (const bf16*)col, (bf16*)dx, B, H, W, C, R, S, stride, pad, Ho, Wo, ldc);
         DFU_CHECK_LAUNCH("col2im_scalar");
     }
     return DFU_OK;

@@ -21,6 +21,7 @@ constexpr int PW_UNROLL = 4;
 template <int OP>
 __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                      bf16* __restrict__ out, long long n) {
+    pdl_sync();
     const long long nv = n >> 3;
     // PW_UNROLL vectors per thread per trip, all loads issued before the first use
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) binary_kernel(const bf16* __restrict__ a,
 
 // Zero fill: 16-byte stores over the aligned body, byte stores for the (at most 15-byte) head and tail.
 __global__ void __launch_bounds__(256) zero_kernel(unsigned char* __restrict__ p, long long bytes) {
+    pdl_sync();
     const long long head = ((16 - ((uintptr_t)p & 15)) & 15) < (unsigned long long)bytes ? ((16 - ((uintptr_t)p & 15)) & 15) : bytes;
     const long long nv = (bytes - head) >> 4;
     uint4* body = reinterpret_cast<uint4*>(p + head);
@@ -86,6 +88,7 @@ constexpr int GB_UNROLL = 4;
 __global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
                                                               bf16* __restrict__ dx, float* __restrict__ colsum, long long M,
                                                               int N) {
+    pdl_sync();
     __shared__ float red[128][9];
     const int cvl = threadIdx.x & 127, rl = threadIdx.x >> 7;
     const int cv = blockIdx.y * 128 + cvl;                 // column vector (8 columns)
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const bf16* __rest
 // Column sums of x[M, N] (row stride ld) added into out[N].  Block = 32 column-vectors x 8 row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M, int N,
                                                      long long ld, int rows_per_block) {
+    pdl_sync();
     __shared__ float red[8][32][9];
     const int cvl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int cv = blockIdx.x * 32 + cvl;              // column vector (8 columns)
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 }
 __global__ void __launch_bounds__(256) colsum_scalar_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M,
                                                             int N, long long ld) {
+    pdl_sync();
     // small / unaligned N: one thread per column, rows split over blockIdx.y
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= N) return;
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(256) colsum_scalar_kernel(const bf16* __restri
 
 __global__ void __launch_bounds__(256) copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst,
                                                      long long ldd, long long rows, int cols, int vec) {
+    pdl_sync();
     if (vec) {
         const int cv = cols >> 3;
         GRID_STRIDE(t, rows * cv) {
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const bf16* __restrict__ sr
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
                                                             long long rows, int cols, long long ldo) {
+    pdl_sync();
     GRID_STRIDE(t, rows * ldo) {
         const long long r = t / ldo;
         const int c = (int)(t % ldo);
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(256) cast_f32_bf16_flat_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
                                                                  long long n) {
+    pdl_sync();
     const long long nv = n >> 3;
     GRID_STRIDE(i, nv) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i * 2);
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_flat_kernel(const float* __
         for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
 }
 __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+    pdl_sync();
     GRID_STRIDE(i, n) dst[i] = __bfloat162float(src[i]);
 }
 
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const bf16* __restrict__ x
                                                       uint8_t* __restrict__ mask, long long n, float p,
                                                       const unsigned long long* __restrict__ seed_dev,
                                                       unsigned long long stream_id) {
+    pdl_sync();
     const uint64_t seed = seed_dev ? *seed_dev : 0ull;
     const float inv_keep = 1.f / (1.f - p);
     GRID_STRIDE(i, n) {
@@ -260,15 +270,18 @@ __global__ void __launch_bounds__(256) dropout_kernel(const bf16* __restrict__ x
 }
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ mask,
                                                           bf16* __restrict__ dx, long long n, float p) {
+    pdl_sync();
     const float inv_keep = 1.f / (1.f - p);
     GRID_STRIDE(i, n) dx[i] = __float2bfloat16(mask[i] ? __bfloat162float(dy[i]) * inv_keep : 0.f);
 }
-__global__ void tick_u64_kernel(unsigned long long* c) { *c += 1ull; }
+__global__ void tick_u64_kernel(unsigned long long* c) {
+    pdl_sync(); *c += 1ull; }
 
 // ViT token assembly (timm VisionTransformer._pos_embed): cls + pos, patches + pos.
 __global__ void __launch_bounds__(256) vit_assemble_kernel(const bf16* __restrict__ patch_out, const float* __restrict__ cls,
                                                            const float* __restrict__ pos, bf16* __restrict__ tokens, int B,
                                                            int T, int D) {
+    pdl_sync();
     const int dv = D >> 3;
     GRID_STRIDE(t, (long long)B * T * dv) {
         const int v = (int)(t % dv);
@@ -291,6 +304,7 @@ __global__ void __launch_bounds__(256) vit_assemble_kernel(const bf16* __restric
 __global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const bf16* __restrict__ dtok, bf16* __restrict__ dpatch,
                                                                float* __restrict__ dcls, float* __restrict__ dpos, int B,
                                                                int T, int D) {
+    pdl_sync();
     const int dv = D >> 3;
     GRID_STRIDE(t, (long long)T * dv) {
         const int v = (int)(t % dv);
@@ -317,6 +331,7 @@ __global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const bf16* __res
 // ------------------------------------------------------------------ pooling
 __global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                       uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+    pdl_sync();
     // one thread = 8 channels of one output pixel; the nine window loads are issued before any is consumed
     const int cv = C >> 3;
     const unsigned total = (unsigned)B * Ho * Wo * cv;            // host checks < 2^31
@@ -361,6 +376,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x
 // (taps of the parity of h+1 / w+1); their winner bytes and gradients are loaded before any is consumed.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dy,
                                                           bf16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
+    pdl_sync();
     const int cv = C >> 3;
     const unsigned total = (unsigned)B * H * W * cv;              // host checks < 2^31
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -413,6 +429,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restr
 
 __global__ void __launch_bounds__(256) avgpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int HW, int C,
                                                       long long ldo) {
+    pdl_sync();
     const int cv = C >> 3;
     GRID_STRIDE(t, (long long)B * cv) {
         const int v = (int)(t % cv);
@@ -434,6 +451,7 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const bf16* __restrict__ x
 }
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const bf16* __restrict__ dout, long long ldo, bf16* __restrict__ dx,
                                                           int B, int HW, int C) {
+    pdl_sync();
     const int cv = C >> 3;
     const float inv = 1.f / (float)HW;
     GRID_STRIDE(t, (long long)B * HW * cv) {
@@ -454,7 +472,7 @@ template <int OP>
 int launch_binary(const void* a, const void* b, void* out, long long n, void* stream, const char* name) {
     DFU_CHECK_ARG(a && out && n > 0 && (OP == 0 || OP == 4 || b), "%s: bad args", name);
     DFU_CHECK_ARG(al16(a) && al16(out) && (OP == 0 || OP == 4 || al16(b)), "%s: buffers must be 16-byte aligned", name);
-    binary_kernel<OP><<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+    dfu_launch(binary_kernel<OP>, grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b, (bf16*)out, n);
     DFU_CHECK_LAUNCH(name);
     return DFU_OK;
 }
@@ -464,7 +482,7 @@ int launch_binary(const void* a, const void* b, void* out, long long n, void* st
 extern "C" int dfu_zero(void* p, int64_t bytes, void* stream) {
     DFU_CHECK_ARG(p && bytes >= 0, "dfu_zero: bad args");
     if (bytes == 0) return DFU_OK;
-    zero_kernel<<<grid_for((bytes + 15) / 16, 256), 256, 0, (cudaStream_t)stream>>>((unsigned char*)p, bytes);
+    dfu_launch(zero_kernel, grid_for((bytes + 15) / 16, 256), 256, 0, (cudaStream_t)stream, (unsigned char*)p, bytes);
     DFU_CHECK_LAUNCH("dfu_zero");
     return DFU_OK;
 }
@@ -488,8 +506,7 @@ extern "C" int dfu_gelu_bwd_colsum(const void* dy, const void* h, void* dx, floa
     const long long max_xb = (M + 1) / 2;
     if (xb > max_xb) xb = max_xb;
     if (xb < 1) xb = 1;
-    gelu_bwd_colsum_kernel<<<dim3((unsigned)xb, (unsigned)ycnt), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dy, (const bf16*)h, (bf16*)dx, colsum, M, N);
+    dfu_launch(gelu_bwd_colsum_kernel, dim3((unsigned)xb, (unsigned)ycnt), 256, 0, (cudaStream_t)stream, (const bf16*)dy, (const bf16*)h, (bf16*)dx, colsum, M, N);
     DFU_CHECK_LAUNCH("dfu_gelu_bwd_colsum");
     return DFU_OK;
 }
@@ -503,10 +520,10 @@ extern "C" int dfu_colsum(const void* x, float* out, int64_t M, int32_t N, int64
         if (row_blocks < 1) row_blocks = 1;
         const int rows_per_block = (int)((M + row_blocks - 1) / row_blocks);
         dim3 grid(col_blocks, dfu_cdiv(M, rows_per_block));
-        colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, out, M, N, ld, rows_per_block);
+        dfu_launch(colsum_kernel, grid, 256, 0, st, (const bf16*)x, out, M, N, ld, rows_per_block);
     } else {
         dim3 grid(dfu_cdiv(N, 64), (unsigned)(M < 256 ? M : 256));
-        colsum_scalar_kernel<<<grid, 64, 0, st>>>((const bf16*)x, out, M, N, ld);
+        dfu_launch(colsum_scalar_kernel, grid, 64, 0, st, (const bf16*)x, out, M, N, ld);
     }
     DFU_CHECK_LAUNCH("dfu_colsum");
     return DFU_OK;
@@ -516,7 +533,7 @@ extern "C" int dfu_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, 
     DFU_CHECK_ARG(src && dst && rows > 0 && cols > 0, "dfu_copy2d: bad args");
     const int vec = (cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && al16(src) && al16(dst)) ? 1 : 0;
     const long long items = vec ? rows * (cols / 8) : rows * cols;
-    copy2d_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, vec);
+    dfu_launch(copy2d_kernel, grid_for(items, 256), 256, 0, (cudaStream_t)stream, (const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, vec);
     DFU_CHECK_LAUNCH("dfu_copy2d");
     return DFU_OK;
 }
@@ -525,16 +542,16 @@ extern "C" int dfu_cast_f32_bf16(const float* src, void* dst, int64_t rows, int3
     DFU_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ldo >= cols, "dfu_cast_f32_bf16: bad args");
     if (ldo == cols && al16(src) && al16(dst)) {
         const long long n = rows * cols;
-        cast_f32_bf16_flat_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+        dfu_launch(cast_f32_bf16_flat_kernel, grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
     } else {
-        cast_f32_bf16_kernel<<<grid_for(rows * ldo, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, rows, cols, ldo);
+        dfu_launch(cast_f32_bf16_kernel, grid_for(rows * ldo, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, rows, cols, ldo);
     }
     DFU_CHECK_LAUNCH("dfu_cast_f32_bf16");
     return DFU_OK;
 }
 extern "C" int dfu_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
     DFU_CHECK_ARG(src && dst && n > 0, "dfu_cast_bf16_f32: bad args");
-    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+    dfu_launch(cast_bf16_f32_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)src, dst, n);
     DFU_CHECK_LAUNCH("dfu_cast_bf16_f32");
     return DFU_OK;
 }
@@ -542,20 +559,20 @@ extern "C" int dfu_cast_bf16_f32(const void* src, float* dst, int64_t n, void* s
 extern "C" int dfu_dropout(const void* x, void* y, uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev,
                            uint64_t stream_id, void* stream) {
     DFU_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dfu_dropout: bad args (p=%f)", p);
-    dropout_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, mask, n, p,
+    dfu_launch(dropout_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, mask, n, p,
                                                                       (const unsigned long long*)seed_dev, stream_id);
     DFU_CHECK_LAUNCH("dfu_dropout");
     return DFU_OK;
 }
 extern "C" int dfu_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, void* stream) {
     DFU_CHECK_ARG(dy && mask && dx && n > 0 && p >= 0.f && p < 1.f, "dfu_dropout_bwd: bad args");
-    dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, mask, (bf16*)dx, n, p);
+    dfu_launch(dropout_bwd_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)dy, mask, (bf16*)dx, n, p);
     DFU_CHECK_LAUNCH("dfu_dropout_bwd");
     return DFU_OK;
 }
 extern "C" int dfu_tick_u64(uint64_t* counter, void* stream) {
     DFU_CHECK_ARG(counter, "dfu_tick_u64: null");
-    tick_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)counter);
+    dfu_launch(tick_u64_kernel, 1, 1, 0, (cudaStream_t)stream, (unsigned long long*)counter);
     DFU_CHECK_LAUNCH("dfu_tick_u64");
     return DFU_OK;
 }
@@ -563,16 +580,14 @@ extern "C" int dfu_tick_u64(uint64_t* counter, void* stream) {
 extern "C" int dfu_vit_assemble(const void* patch_out, const float* cls, const float* pos, void* tokens, int32_t B, int32_t T,
                                 int32_t D, void* stream) {
     DFU_CHECK_ARG(patch_out && cls && pos && tokens && B > 0 && T > 1 && D % 8 == 0, "dfu_vit_assemble: bad args");
-    vit_assemble_kernel<<<grid_for((long long)B * T * (D / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)patch_out, cls, pos, (bf16*)tokens, B, T, D);
+    dfu_launch(vit_assemble_kernel, grid_for((long long)B * T * (D / 8), 256), 256, 0, (cudaStream_t)stream, (const bf16*)patch_out, cls, pos, (bf16*)tokens, B, T, D);
     DFU_CHECK_LAUNCH("dfu_vit_assemble");
     return DFU_OK;
 }
 extern "C" int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dcls, float* dpos, int32_t B, int32_t T,
                                     int32_t D, void* stream) {
     DFU_CHECK_ARG(dtokens && dcls && dpos && B > 0 && T > 1 && D % 8 == 0, "dfu_vit_assemble_bwd: bad args");
-    vit_assemble_bwd_kernel<<<grid_for((long long)T * (D / 8), 64, 32), 64, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dtokens, (bf16*)dpatch, dcls, dpos, B, T, D);
+    dfu_launch(vit_assemble_bwd_kernel, grid_for((long long)T * (D / 8), 64, 32), 64, 0, (cudaStream_t)stream, (const bf16*)dtokens, (bf16*)dpatch, dcls, dpos, B, T, D);
     DFU_CHECK_LAUNCH("dfu_vit_assemble_bwd");
     return DFU_OK;
 }
@@ -580,7 +595,7 @@ extern "C" int dfu_vit_assemble_bwd(const void* dtokens, void* dpatch, float* dc
 extern "C" int dfu_maxpool3x3s2(const void* x, void* y, uint8_t* idx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
     DFU_CHECK_ARG(x && y && B > 0 && C % 8 == 0 && (long long)B * H * W * (C / 8) < (1ll << 31), "dfu_maxpool3x3s2: bad args");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, idx,
+    dfu_launch(maxpool_kernel, grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, idx,
                                                                                                      B, H, W, C, Ho, Wo);
     DFU_CHECK_LAUNCH("dfu_maxpool3x3s2");
     return DFU_OK;
@@ -590,20 +605,20 @@ extern "C" int dfu_maxpool3x3s2_bwd(const uint8_t* idx, const void* dy, void* dx
     DFU_CHECK_ARG(idx && dy && dx && B > 0 && C % 8 == 0 && (long long)B * H * W * (C / 8) < (1ll << 31),
                   "dfu_maxpool3x3s2_bwd: bad args");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    maxpool_bwd_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(idx, (const bf16*)dy,
+    dfu_launch(maxpool_bwd_kernel, grid_for((long long)B * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream, idx, (const bf16*)dy,
                                                                                                        (bf16*)dx, B, H, W, C, Ho, Wo);
     DFU_CHECK_LAUNCH("dfu_maxpool3x3s2_bwd");
     return DFU_OK;
 }
 extern "C" int dfu_avgpool(const void* x, void* out, int32_t B, int32_t HW, int32_t C, int64_t ldo, void* stream) {
     DFU_CHECK_ARG(x && out && B > 0 && HW > 0 && C % 8 == 0 && ldo % 8 == 0 && al16(out), "dfu_avgpool: bad args");
-    avgpool_kernel<<<grid_for((long long)B * (C / 8), 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, B, HW, C, ldo);
+    dfu_launch(avgpool_kernel, grid_for((long long)B * (C / 8), 128), 128, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, B, HW, C, ldo);
     DFU_CHECK_LAUNCH("dfu_avgpool");
     return DFU_OK;
 }
 extern "C" int dfu_avgpool_bwd(const void* dout, int64_t ldo, void* dx, int32_t B, int32_t HW, int32_t C, void* stream) {
     DFU_CHECK_ARG(dout && dx && B > 0 && HW > 0 && C % 8 == 0 && ldo % 8 == 0 && al16(dout), "dfu_avgpool_bwd: bad args");
-    avgpool_bwd_kernel<<<grid_for((long long)B * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, ldo, (bf16*)dx,
+    dfu_launch(avgpool_bwd_kernel, grid_for((long long)B * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream, (const bf16*)dout, ldo, (bf16*)dx,
                                                                                                     B, HW, C);
     DFU_CHECK_LAUNCH("dfu_avgpool_bwd");
     return DFU_OK;

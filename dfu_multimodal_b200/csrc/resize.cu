@@ -25,6 +25,7 @@ struct Norm3 {
 
 // Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc, bilinear filter, full-image box.  One thread per output index.
 __global__ void resize_coeffs_kernel(int in_size, int out_size, int ksize, int* __restrict__ bounds, int* __restrict__ coeffs) {
+    pdl_sync();
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     if (xx >= out_size) return;
     const double scale = __ddiv_rn((double)in_size, (double)out_size);
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
                                                         const int* __restrict__ hbounds, const int* __restrict__ hcoef, int hks,
                                                         const int* __restrict__ vbounds, const int* __restrict__ vcoef, int vks,
                                                         int OH, int OW, int band, int max_rows, void* __restrict__ out, Norm3 nm) {
+    pdl_sync();
     extern __shared__ uint8_t tmp[];                     // [rows of the band][OW*3]
     const int b = blockIdx.y;
     const int y0 = blockIdx.x * band, y1 = min(OH, y0 + band);
@@ -143,8 +145,8 @@ extern "C" int dfu_resize_u8(const uint8_t* src, int64_t img_stride_bytes, int32
     int* hcoef = hbounds + OW * 2;
     int* vbounds = hcoef + OW * hks;
     int* vcoef = vbounds + OH * 2;
-    resize_coeffs_kernel<<<dfu_cdiv(OW, 128), 128, 0, st>>>(Ws, OW, hks, hbounds, hcoef);
-    resize_coeffs_kernel<<<dfu_cdiv(OH, 128), 128, 0, st>>>(Hs, OH, vks, vbounds, vcoef);
+    dfu_launch(resize_coeffs_kernel, dfu_cdiv(OW, 128), 128, 0, st, Ws, OW, hks, hbounds, hcoef);
+    dfu_launch(resize_coeffs_kernel, dfu_cdiv(OH, 128), 128, 0, st, Hs, OH, vks, vbounds, vcoef);
     DFU_CHECK_LAUNCH("dfu_resize_u8 coefficients");
     // band of output rows per CTA: the largest whose input rows (band * scale + 2 * support + 2, the bound of Pillow's
     // xmin/xmax formulas) fit in shared memory
@@ -168,7 +170,7 @@ extern "C" int dfu_resize_u8(const uint8_t* src, int64_t img_stride_bytes, int32
 #define RS_LAUNCH(MODE)                                                                                                            \
     do {                                                                                                                           \
         if (smem > 48 * 1024) cudaFuncSetAttribute(resize_u8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        resize_u8_kernel<MODE><<<grid, 256, smem, st>>>(src, img_stride_bytes, Hs, Ws, hbounds, hcoef, hks, vbounds, vcoef, vks,   \
+        dfu_launch(resize_u8_kernel<MODE>, grid, 256, smem, st, src, img_stride_bytes, Hs, Ws, hbounds, hcoef, hks, vbounds, vcoef, vks,   \
                                                         OH, OW, band, max_rows, out, nm);                                          \
     } while (0)
     if (out_mode == 0) RS_LAUNCH(0);

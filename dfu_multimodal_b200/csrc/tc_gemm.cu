@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_x,
                    const GemmParams p) {
+    pdl_trigger();        // the next kernel of the stream may be scheduled as soon as this grid is resident (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES];
     __shared__ uint64_t empty_bar[MAX_STAGES];
@@ -331,6 +332,8 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // barriers, TMEM and tensor-map prefetch are set up: only now wait for the previous kernel's results
+    pdl_wait();
 
     // bytes landing per ring stage: both CTAs' tiles are counted on the leader's barrier
     const int bn_cta = p.block_n / CG;                              // B-tile rows (N columns) staged by this CTA
@@ -900,6 +903,7 @@ struct RefParams {
 };
 
 __global__ void __launch_bounds__(256) dfu_ref_gemm_kernel(const RefParams p) {
+    pdl_sync();
     __shared__ float As[16][17];
     __shared__ float Bs[16][17];
     const int z = blockIdx.z;
@@ -1115,13 +1119,15 @@ void launch_pair(int grid, cudaStream_t stream, const CUtensorMap& ma, const CUt
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = dfu_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     (void)cudaLaunchKernelEx(&cfg, dfu_tc_gemm_kernel<CS, EM, 2>, ma, mb, md, mx, p);
 }
 
@@ -1143,20 +1149,20 @@ void launch_gemm(int em, int grid, cudaStream_t stream, const CUtensorMap& ma, c
         }
     }
     switch (em) {
-        case -1: dfu_tc_gemm_kernel<true, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case -2: dfu_tc_gemm_kernel<true, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 1: dfu_tc_gemm_kernel<false, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 2: dfu_tc_gemm_kernel<false, 2, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 3: dfu_tc_gemm_kernel<false, 3, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 4: dfu_tc_gemm_kernel<false, 4, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 5: dfu_tc_gemm_kernel<false, 5, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 6: dfu_tc_gemm_kernel<false, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case -6: dfu_tc_gemm_kernel<true, 6, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 7: dfu_tc_gemm_kernel<false, 7, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 8: dfu_tc_gemm_kernel<false, 8, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 9: dfu_tc_gemm_kernel<false, 9, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        case 10: dfu_tc_gemm_kernel<false, 10, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
-        default: dfu_tc_gemm_kernel<false, 0, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, md, mx, p); break;
+        case -1: dfu_launch(dfu_tc_gemm_kernel<true, 0, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case -2: dfu_launch(dfu_tc_gemm_kernel<true, 1, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 1: dfu_launch(dfu_tc_gemm_kernel<false, 1, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 2: dfu_launch(dfu_tc_gemm_kernel<false, 2, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 3: dfu_launch(dfu_tc_gemm_kernel<false, 3, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 4: dfu_launch(dfu_tc_gemm_kernel<false, 4, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 5: dfu_launch(dfu_tc_gemm_kernel<false, 5, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 6: dfu_launch(dfu_tc_gemm_kernel<false, 6, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case -6: dfu_launch(dfu_tc_gemm_kernel<true, 6, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 7: dfu_launch(dfu_tc_gemm_kernel<false, 7, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 8: dfu_launch(dfu_tc_gemm_kernel<false, 8, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 9: dfu_launch(dfu_tc_gemm_kernel<false, 9, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        case 10: dfu_launch(dfu_tc_gemm_kernel<false, 10, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
+        default: dfu_launch(dfu_tc_gemm_kernel<false, 0, 1>, grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, md, mx, p); break;
     }
 }
 
@@ -1198,7 +1204,7 @@ extern "C" int dfu_gemm(const dfu_gemm_args* a, void* stream_) {
         dim3 grid(dfu_cdiv(a->N, 16), dfu_cdiv(a->M, 16), a->nb0 * a->nb1);
         DFU_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "dfu_gemm(simt): grid too large (M=%d, batch=%d)", a->M,
                       a->nb0 * a->nb1);
-        dfu_ref_gemm_kernel<<<grid, 256, 0, stream>>>(p);
+        dfu_launch(dfu_ref_gemm_kernel, grid, 256, 0, stream, p);
         DFU_CHECK_LAUNCH("dfu_ref_gemm_kernel");
         return DFU_OK;
     }

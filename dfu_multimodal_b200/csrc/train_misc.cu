@@ -16,6 +16,7 @@ inline int grid_for(long long items, int threads, int per_sm = 8) {
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                             const float* __restrict__ weight, float* __restrict__ loss,
                                                             float* __restrict__ dlogits, int B, int C) {
+    pdl_sync();
     __shared__ float red[32];
     float wsum = 0.f, lsum = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) predict_kernel(const float* __restrict__ logits, float* __restrict__ prob1,
                                                       long long* __restrict__ pred, int B, int C) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float* row = logits + (long long)b * C;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(256) predict_kernel(const float* __restrict__ 
 // out[i] = a[i] * (*s)   (fp32; upstream scalar gradient of the loss)
 __global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __restrict__ a, const float* __restrict__ s,
                                                               float* __restrict__ out, long long n) {
+    pdl_sync();
     const float k = *s;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = a[i] * k;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
                                                          float* __restrict__ v, bf16* __restrict__ shadow, long long n,
                                                          const float* __restrict__ step, float lr, float b1, float b2,
                                                          float eps, float wd, float gscale) {
+    pdl_sync();
     const float t = *step;
     const float bc1 = 1.f - powf(b1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const dfu_adamw_tensor
                                                           const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_offset,
                                                           int chunk_size, const float* __restrict__ step, float lr, float b1,
                                                           float b2, float eps, float wd, float gscale) {
+    pdl_sync();
     const dfu_adamw_tensor t = table[chunk_tensor[blockIdx.x]];
     const long long start = (long long)chunk_offset[blockIdx.x] * chunk_size;
     const long long end = min(start + chunk_size, (long long)t.numel);
@@ -192,12 +197,14 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const dfu_adamw_tensor
         }
     }
 }
-__global__ void tick_f32_kernel(float* s) { *s += 1.f; }
+__global__ void tick_f32_kernel(float* s) {
+    pdl_sync(); *s += 1.f; }
 
 // ------------------------------------------------------------------ Grad-CAM reduction (single block)
 // w_c = mean_hw G[hw, c]; cam[hw] = relu(sum_{c<nc} w_c * A[hw, c]); cam /= max if max > 0.
 __global__ void __launch_bounds__(256) gradcam_kernel(const bf16* __restrict__ A, int CA, const bf16* __restrict__ G, int CG, int HW,
                                                       int nc, float* __restrict__ cam) {
+    pdl_sync();
     extern __shared__ float sh[];           // w[nc] then cam[HW]
     __shared__ float red[32];
     float* w = sh;
@@ -226,6 +233,7 @@ __global__ void __launch_bounds__(256) gradcam_kernel(const bf16* __restrict__ A
 // saliency: out[hw] = mean_c |d[c, hw]|, then / max (two kernels: the max is grid wide)
 __global__ void __launch_bounds__(256) saliency_kernel(const float* __restrict__ d, float* __restrict__ out, float* __restrict__ mx,
                                                        int C, int HW) {
+    pdl_sync();
     __shared__ float red[32];
     float local = 0.f;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(256) saliency_kernel(const float* __restrict__
     if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(mx), __float_as_int(local));   // values >= 0
 }
 __global__ void __launch_bounds__(256) saliency_norm_kernel(float* __restrict__ out, const float* __restrict__ mx, int HW) {
+    pdl_sync();
     const float m = *mx;
     if (!(m > 0.f)) return;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) out[p] /= m;
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(256) saliency_norm_kernel(float* __restrict__ 
 
 __global__ void __launch_bounds__(256) tta_vote_kernel(const float* __restrict__ probs, float* __restrict__ mean_prob,
                                                        long long* __restrict__ pred, int n, int V) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f, votes = 0.f;
@@ -263,26 +273,26 @@ __global__ void __launch_bounds__(256) tta_vote_kernel(const float* __restrict__
 extern "C" int dfu_cross_entropy(const float* logits, const int64_t* labels, const float* weight, float* loss, float* dlogits,
                                  int32_t B, int32_t C, void* stream) {
     DFU_CHECK_ARG(logits && labels && B > 0 && C > 0 && (loss || dlogits), "dfu_cross_entropy: bad args");
-    cross_entropy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)labels, weight, loss, dlogits, B, C);
+    dfu_launch(cross_entropy_kernel, 1, 256, 0, (cudaStream_t)stream, logits, (const long long*)labels, weight, loss, dlogits, B, C);
     DFU_CHECK_LAUNCH("dfu_cross_entropy");
     return DFU_OK;
 }
 extern "C" int dfu_predict(const float* logits, float* prob1, int64_t* pred, int32_t B, int32_t C, void* stream) {
     DFU_CHECK_ARG(logits && B > 0 && C > 0, "dfu_predict: bad args");
-    predict_kernel<<<dfu_cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(logits, prob1, (long long*)pred, B, C);
+    dfu_launch(predict_kernel, dfu_cdiv(B, 256), 256, 0, (cudaStream_t)stream, logits, prob1, (long long*)pred, B, C);
     DFU_CHECK_LAUNCH("dfu_predict");
     return DFU_OK;
 }
 extern "C" int dfu_scale_by_scalar(const float* a, const float* scalar_dev, float* out, int64_t n, void* stream) {
     DFU_CHECK_ARG(a && scalar_dev && out && n > 0, "dfu_scale_by_scalar: bad args");
-    scale_by_scalar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, scalar_dev, out, n);
+    dfu_launch(scale_by_scalar_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, a, scalar_dev, out, n);
     DFU_CHECK_LAUNCH("dfu_scale_by_scalar");
     return DFU_OK;
 }
 
 extern "C" int dfu_adamw_tick(float* step, void* stream) {
     DFU_CHECK_ARG(step, "dfu_adamw_tick: null");
-    tick_f32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    dfu_launch(tick_f32_kernel, 1, 1, 0, (cudaStream_t)stream, step);
     DFU_CHECK_LAUNCH("dfu_adamw_tick");
     return DFU_OK;
 }
@@ -292,10 +302,10 @@ extern "C" int dfu_adamw(const dfu_adamw_tensor* table, int32_t n_tensors, const
     DFU_CHECK_ARG(table && n_tensors > 0 && chunk_tensor && chunk_offset && n_chunks > 0 && chunk_size > 0 && chunk_size % 4 == 0 && step,
                   "dfu_adamw: bad args");
     if (g_bf16)
-        adamw_multi_kernel<true><<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, chunk_tensor, chunk_offset, chunk_size, step, lr,
+        dfu_launch(adamw_multi_kernel<true>, n_chunks, 256, 0, (cudaStream_t)stream, table, chunk_tensor, chunk_offset, chunk_size, step, lr,
                                                                             beta1, beta2, eps, weight_decay, grad_scale);
     else
-        adamw_multi_kernel<false><<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, chunk_tensor, chunk_offset, chunk_size, step, lr,
+        dfu_launch(adamw_multi_kernel<false>, n_chunks, 256, 0, (cudaStream_t)stream, table, chunk_tensor, chunk_offset, chunk_size, step, lr,
                                                                              beta1, beta2, eps, weight_decay, grad_scale);
     DFU_CHECK_LAUNCH("dfu_adamw");
     return DFU_OK;
@@ -307,10 +317,10 @@ extern "C" int dfu_adamw_flat(float* p, const void* g, float* m, float* v, void*
                   "dfu_adamw_flat: buffers must be 16-byte aligned");
     const int grid = grid_for((n + 3) / 4, 256, 8);
     if (g_bf16)
-        adamw_flat_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow, n, step, lr, beta1, beta2, eps,
+        dfu_launch(adamw_flat_kernel<true>, grid, 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)shadow, n, step, lr, beta1, beta2, eps,
                                                                        weight_decay, grad_scale);
     else
-        adamw_flat_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)shadow, n, step, lr, beta1, beta2, eps,
+        dfu_launch(adamw_flat_kernel<false>, grid, 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)shadow, n, step, lr, beta1, beta2, eps,
                                                                         weight_decay, grad_scale);
     DFU_CHECK_LAUNCH("dfu_adamw_flat");
     return DFU_OK;
@@ -320,7 +330,7 @@ extern "C" int dfu_gradcam(const void* A, int32_t CA, const void* G, int32_t CG,
     DFU_CHECK_ARG(A && G && cam && HW > 0 && nc > 0 && nc <= CA && nc <= CG, "dfu_gradcam: bad args");
     const size_t smem = (size_t)(nc + HW) * sizeof(float);
     DFU_CHECK_ARG(smem <= 48 * 1024, "dfu_gradcam: nc+HW too large (%d + %d)", nc, HW);
-    gradcam_kernel<<<1, 256, smem, (cudaStream_t)stream>>>((const bf16*)A, CA, (const bf16*)G, CG, HW, nc, cam);
+    dfu_launch(gradcam_kernel, 1, 256, smem, (cudaStream_t)stream, (const bf16*)A, CA, (const bf16*)G, CG, HW, nc, cam);
     DFU_CHECK_LAUNCH("dfu_gradcam");
     return DFU_OK;
 }
@@ -329,15 +339,15 @@ extern "C" int dfu_saliency(const float* dimg, float* out, float* max_scratch, i
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(max_scratch, 0, sizeof(float), st);
     const int grid = grid_for(HW, 256, 2);
-    saliency_kernel<<<grid, 256, 0, st>>>(dimg, out, max_scratch, C, HW);
+    dfu_launch(saliency_kernel, grid, 256, 0, st, dimg, out, max_scratch, C, HW);
     DFU_CHECK_LAUNCH("dfu_saliency");
-    saliency_norm_kernel<<<grid, 256, 0, st>>>(out, max_scratch, HW);
+    dfu_launch(saliency_norm_kernel, grid, 256, 0, st, out, max_scratch, HW);
     DFU_CHECK_LAUNCH("dfu_saliency_norm");
     return DFU_OK;
 }
 extern "C" int dfu_tta_vote(const float* probs, float* mean_prob, int64_t* pred, int32_t n, int32_t V, void* stream) {
     DFU_CHECK_ARG(probs && mean_prob && pred && n > 0 && V > 0, "dfu_tta_vote: bad args");
-    tta_vote_kernel<<<dfu_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(probs, mean_prob, (long long*)pred, n, V);
+    dfu_launch(tta_vote_kernel, dfu_cdiv(n, 256), 256, 0, (cudaStream_t)stream, probs, mean_prob, (long long*)pred, n, V);
     DFU_CHECK_LAUNCH("dfu_tta_vote");
     return DFU_OK;
 }

@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(256) v32_patchify_kernel(const float* __restri
         out[t] = x[(((long long)b * 224 + ph * 16 + i) * 224 + pw * 16 + j) * 3 + c];
     }
 }
+// x <- float(bf16(x)): what storing an activation (or a weight shadow) as bf16 does to it
+__global__ void __launch_bounds__(256) v32_round_bf16_kernel(float* __restrict__ x, long long n) {
+    V32_LOOP(i, n) x[i] = __bfloat162float(__float2bfloat16(x[i]));
+}
 __global__ void __launch_bounds__(256) v32_copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
                                                          long long rows, int cols) {
     V32_LOOP(i, rows * cols) dst[(i / cols) * ldd + i % cols] = src[(i / cols) * lds + i % cols];
@@ -255,6 +259,12 @@ extern "C" int dfu_v32_copy2d(const float* src, int64_t lds, float* dst, int64_t
     DFU_CHECK_ARG(src && dst && rows > 0 && cols > 0, "dfu_v32_copy2d: bad args");
     v32_copy2d_kernel<<<v32_grid(rows * cols), 256, 0, V32_ST>>>(src, lds, dst, ldd, rows, cols);
     DFU_CHECK_LAUNCH("dfu_v32_copy2d");
+    return DFU_OK;
+}
+extern "C" int dfu_v32_round_bf16(float* x, int64_t n, void* stream) {
+    DFU_CHECK_ARG(x && n > 0, "dfu_v32_round_bf16: bad args");
+    v32_round_bf16_kernel<<<v32_grid(n), 256, 0, V32_ST>>>(x, n);
+    DFU_CHECK_LAUNCH("dfu_v32_round_bf16");
     return DFU_OK;
 }
 extern "C" int dfu_v32_vit_assemble(const float* patch_out, const float* cls, const float* pos, float* tokens, int32_t B, int32_t T, int32_t D,

@@ -54,6 +54,7 @@ class GradBucketer:
         self.producers = [set() for _ in self.buckets]
         self.got = set()          # parameters that produced a gradient since begin_step()
         self.works = []
+        self.events = [None] * len(self.buckets)     # bucket -> CUDA event recorded behind its all-reduce
         self.is_cuda = params[0].is_cuda
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream() if self.is_cuda else None)
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
@@ -64,6 +65,7 @@ class GradBucketer:
         self.producers = [set() for _ in self.buckets]
         self.got = set()
         self.works = []
+        self.events = [None] * len(self.buckets)
 
     def _on_grad(self, p):
         bi, off, n = self.slot[p]
@@ -90,11 +92,38 @@ class GradBucketer:
                 self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(flat, op=op, group=self.pg)
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                self.events[bi] = ev
         else:
             self.works.append(dist.all_reduce(flat, op=op, group=self.pg, async_op=True))
 
+    def bucket_of(self, p):
+        return self.slot[p][0] if p in self.slot else None
+
+    def wait_bucket(self, bi):
+        """The current stream waits for bucket `bi`'s all-reduce only (FusedAdamW updates bucket by bucket, so the update of
+        the early buckets runs while the last all-reduces are still on the wire)."""
+        if self.is_cuda and self.events[bi] is not None:
+            torch.cuda.current_stream().wait_event(self.events[bi])
+
+    def flush(self):
+        """Launch the all-reduce of every bucket that is still waiting for gradients that will not come (frozen or unused
+        parameters); does NOT wait for any collective."""
+        self._flush_pending()
+
     def finish_step(self):
         """All buckets reduced and visible to the current stream."""
+        self._flush_pending()
+        if self.is_cuda:
+            if self.world > 1:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            for w in self.works:
+                w.wait()
+            self.works = []
+
+    def _flush_pending(self):
         for bi, left in enumerate(self.pending):
             if left > 0:
                 # some parameters of this bucket received no gradient this step (frozen or conditionally used): their
@@ -106,13 +135,6 @@ class GradBucketer:
                         self.flat[bi][off:off + n].zero_()
                 self.pending[bi] = 0
                 self._launch(bi)
-        if self.is_cuda:
-            if self.world > 1:
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
-        else:
-            for w in self.works:
-                w.wait()
-            self.works = []
 
     def grad_source(self, p):
         """For FusedAdamW.set_grad_source: (bf16 grad slice, is_bf16, scale)."""

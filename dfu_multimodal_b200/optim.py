@@ -19,12 +19,15 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}      # (group index, pointer signature) -> cached device table
         self._grad_source = None
+        self._bucketer = None
         self._steps = {}       # (device type, index) -> fp32 device scalar shared by every parameter on that device
 
-    def set_grad_source(self, source):
+    def set_grad_source(self, source, bucketer=None):
         """source(p) -> (tensor_with_grad_in_storage_order, is_bf16, scale): lets the data-parallel bucketer hand
-        the all-reduced bf16 buckets straight to the update kernel."""
+        the all-reduced bf16 buckets straight to the update kernel.  With `bucketer` (ddp.GradBucketer) the update runs one
+        launch per bucket, each waiting only for ITS bucket's all-reduce."""
         self._grad_source = source
+        self._bucketer = bucketer
         self._tables.clear()
 
     def _state_for(self, p):
@@ -89,7 +92,7 @@ class FusedAdamW(torch.optim.Optimizer):
             # tables built during CUDA-graph capture are baked into that graph (device table, pinned staging buffers) and
             # must outlive it; eager tables are keyed by allocator-dependent gradient addresses, keep only a few
             eager = [k for k, c in self._tables.items() if not c["captured"]]
-            for k in eager[:max(0, len(eager) - 3)]:
+            for k in eager[:max(0, len(eager) - 64)]:
                 del self._tables[k]
             self._tables[key] = cached
         return cached
@@ -171,20 +174,32 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             if len(set((p.device.type, p.device.index) for p in params)) > 1:
                 raise RuntimeError("FusedAdamW: the parameters of one group must live on one device")
-            cached = self._table_for(gi, group, params, grads, g_bf16)
+            # one launch per gradient bucket when a bucketer is attached (each waits for its own all-reduce), else one launch
+            parts = [(None, params, grads)]
+            if self._bucketer is not None:
+                by_bucket = {}
+                for p, g in zip(params, grads):
+                    by_bucket.setdefault(self._bucketer.bucket_of(p), ([], []))
+                    by_bucket[self._bucketer.bucket_of(p)][0].append(p)
+                    by_bucket[self._bucketer.bucket_of(p)][1].append(g)
+                parts = [(bi, ps, gs) for bi, (ps, gs) in sorted(by_bucket.items(), key=lambda kv: (kv[0] is None, kv[0]))]
             b1, b2 = group["betas"]
-            if cached["step"].data_ptr() not in ticked:
-                ticked.add(cached["step"].data_ptr())
-                check(L.dfu_adamw_tick(cached["step"].data_ptr(), st), "adamw_tick")
+            for bi, ps, gs in parts:
+                cached = self._table_for((gi, bi), group, ps, gs, g_bf16)
+                if cached["step"].data_ptr() not in ticked:
+                    ticked.add(cached["step"].data_ptr())
+                    check(L.dfu_adamw_tick(cached["step"].data_ptr(), st), "adamw_tick")
+                    ops._count()
+                if bi is not None:
+                    self._bucketer.wait_bucket(bi)
+                check(L.dfu_adamw(cached["table"].data_ptr(), cached["n"], cached["ct"].data_ptr(), cached["co"].data_ptr(),
+                                  cached["n_chunks"], CHUNK, cached["step"].data_ptr(), group["lr"], b1, b2, group["eps"],
+                                  group["weight_decay"], scale, 1 if cached["g_bf16"] else 0, st), "adamw")
                 ops._count()
-            check(L.dfu_adamw(cached["table"].data_ptr(), cached["n"], cached["ct"].data_ptr(), cached["co"].data_ptr(),
-                              cached["n_chunks"], CHUNK, cached["step"].data_ptr(), group["lr"], b1, b2, group["eps"],
-                              group["weight_decay"], scale, 1 if cached["g_bf16"] else 0, st), "adamw")
-            ops._count()
-            fresh = set(id(p) for p in cached["shadowed"])
-            for p in params:
-                if id(p) in fresh:
-                    mark_shadow_fresh(p)
-                elif getattr(p, "_dfu_shadow", None) is not None:
-                    p._dfu_shadow = (None, p._dfu_shadow[1])     # padded shadow: recast on next use
+                fresh = set(id(p) for p in cached["shadowed"])
+                for p in ps:
+                    if id(p) in fresh:
+                        mark_shadow_fresh(p)
+                    elif getattr(p, "_dfu_shadow", None) is not None:
+                        p._dfu_shadow = (None, p._dfu_shadow[1])     # padded shadow: recast on next use
         return loss

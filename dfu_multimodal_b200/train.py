@@ -37,7 +37,10 @@ class TrainStep:
         loss = cross_entropy(logits, labels, self.class_weights)
         loss.backward()
         if self.bucketer is not None:
-            self.bucketer.finish_step()
+            if getattr(self.optimizer, "_bucketer", None) is self.bucketer:
+                self.bucketer.flush()            # FusedAdamW waits bucket by bucket (optim.py), not for the whole exchange
+            else:
+                self.bucketer.finish_step()
         self.optimizer.step()
         ops.ZERO_ARENA.end_step()
         return loss.detach(), logits.detach()

@@ -23,6 +23,26 @@ from .vit import DfuVisionTransformer
 
 F32 = torch.float32
 
+# forward_fp32(..., emulate_bf16_storage=True): every activation an op of the fast path stores as bf16, and every GEMM weight
+# (the bf16 shadows), is rounded to bf16 precision in place -- fp32 arithmetic, bf16 storage.  The distance of THAT result from
+# the fp32 reference is what bf16 storage alone costs on the given weights; the fast path must sit next to it.
+_EMULATE = [False]
+
+
+def _q(t):
+    """Round an fp32 activation to bf16 precision in place when emulating bf16 storage."""
+    if _EMULATE[0]:
+        check(_L().dfu_v32_round_bf16(_p(t), t.numel(), _st()), "v32_round_bf16")
+        ops._count()
+    return t
+
+
+def _qw(w):
+    """A weight as the fast path sees it: its bf16 shadow (a rounded copy) when emulating, the fp32 master otherwise."""
+    if not _EMULATE[0]:
+        return w.detach()
+    return _q(w.detach().clone())
+
 
 def _L():
     return _lib.load()
@@ -60,8 +80,8 @@ def linear(x2d, weight, bias=None, act=0, res=None):
     N = weight.shape[0]
     assert weight.numel() == N * K
     y = _new((M, N), x2d)
-    return gemm(x2d, weight.detach(), y, M, N, K, (K, 1), (K, 1), N, bias=None if bias is None else bias.detach(), res=res,
-                ldr=N, act=act)
+    return _q(gemm(x2d, _qw(weight), y, M, N, K, (K, 1), (K, 1), N, bias=None if bias is None else bias.detach(), res=res,
+                   ldr=N, act=act))
 
 
 # ------------------------------------------------------------------------------------------------- inputs
@@ -75,20 +95,20 @@ def _image_nhwc(x, kind):
         mean, std = ops._norm_consts(kind)
         check(_L().dfu_v32_preprocess_u8(_p(x.contiguous()), _p(out), B * H * W, mean, std, _st()), "v32_preprocess_u8")
         ops._count()
-        return out
+        return _q(out)
     x = x.float().contiguous()
     B, C, H, W = x.shape
     out = _new((B, H, W, C), x)
     check(_L().dfu_v32_nchw_to_nhwc(_p(x), _p(out), B, C, H, W, _st()), "v32_nchw_to_nhwc")
     ops._count()
-    return out
+    return _q(out)
 
 
 # ------------------------------------------------------------------------------------------------- ResNet50
 def _conv(x, conv):
     """x fp32 NHWC [B,H,W,C]; conv.weight is stored channels_last == [Cout, R*S*Cin]."""
     B, H, W, C = x.shape
-    w = conv.weight.detach()
+    w = conv.weight
     Cout, Cin, R, S = w.shape
     stride, pad = conv.stride[0], conv.padding[0]
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
@@ -102,8 +122,8 @@ def _conv(x, conv):
         ops._count()
     K = R * S * C
     y = _new((B * Ho * Wo, Cout), x)
-    gemm(col, w, y, B * Ho * Wo, Cout, K, (K, 1), (K, 1), Cout)
-    return y.view(B, Ho, Wo, Cout)
+    gemm(col, _qw(w), y, B * Ho * Wo, Cout, K, (K, 1), (K, 1), Cout)
+    return _q(y).view(B, Ho, Wo, Cout)
 
 
 def _bn(y, bn, relu, res=None):
@@ -119,7 +139,7 @@ def _bn(y, bn, relu, res=None):
     check(_L().dfu_v32_bn_apply(_p(y), _p(mean), _p(var), _p(bn.weight.detach()), _p(bn.bias.detach()), _p(res), _p(out), M, C,
                                 1 if relu else 0, bn.eps, _st()), "v32_bn_apply")
     ops._count()
-    return out
+    return _q(out)
 
 
 def _bottleneck(x, blk):
@@ -160,7 +180,7 @@ def resnet_fp32(resnet, x, kind="imagenet"):
     y = _new((B, Ho, Wo, C), x)
     check(_L().dfu_v32_maxpool3x3s2(_p(x), _p(y), B, H, W, C, _st()), "v32_maxpool")
     ops._count()
-    x = y
+    x = y                     # (a max of bf16 values is a bf16 value)
     for layer in (resnet.layer1, resnet.layer2, resnet.layer3, resnet.layer4):
         for blk in layer:
             x = _bottleneck(x, blk)
@@ -168,7 +188,7 @@ def resnet_fp32(resnet, x, kind="imagenet"):
     f = _new((B, C), x)
     check(_L().dfu_v32_avgpool(_p(x), _p(f), B, H * W, C, _st()), "v32_avgpool")
     ops._count()
-    return _head(f, resnet.fc)
+    return _head(_q(f), resnet.fc)
 
 
 # ------------------------------------------------------------------------------------------------- ViT-B/16
@@ -177,7 +197,7 @@ def _layernorm(x2d, ln):
     y = torch.empty_like(x2d)
     check(_L().dfu_v32_layernorm(_p(x2d), _p(ln.weight.detach()), _p(ln.bias.detach()), _p(y), rows, D, ln.eps, _st()), "v32_layernorm")
     ops._count()
-    return y
+    return _q(y)
 
 
 def _attention(x2d, attn, B, T, res):
@@ -191,11 +211,12 @@ def _attention(x2d, attn, B, T, res):
          sd=(T * T, H * T * T), b_off=D)
     check(_L().dfu_v32_softmax_rows(_p(P), B * H * T, T, T, _st()), "v32_softmax_rows")
     ops._count()
+    _q(P)                     # the fused attention kernel feeds P to the tensor cores as bf16
     out = _new((B * T, D), x2d)
     # O = P v: B operand v[t, d] read as B[n=d][k=t]
     gemm(P, qkv, out, T, hd, T, (T, 1), (1, D3), D, nb0=H, nb1=B, sa=(T * T, H * T * T), sb=(hd, T * D3), sd=(hd, T * D),
          b_off=2 * D)
-    return linear(out, attn.proj.weight, attn.proj.bias, res=res)
+    return linear(_q(out), attn.proj.weight, attn.proj.bias, res=res)
 
 
 def vit_fp32(vit, x, kind="half"):
@@ -206,7 +227,7 @@ def vit_fp32(vit, x, kind="half"):
         raise RuntimeError("vit_base_patch16_224 takes 224x224x3 images, got %s" % (tuple(x.shape),))
     patches = _new((B * 196, 768), x)
     check(_L().dfu_v32_patchify(_p(x), _p(patches), B, _st()), "v32_patchify")
-    ops._count()
+    ops._count()                # (a permutation of already rounded values)
     proj = vit.patch_embed.proj
     po = linear(patches, proj.weight, proj.bias)
     T, D = vit.pos_embed.shape[1], vit.pos_embed.shape[2]
@@ -214,6 +235,7 @@ def vit_fp32(vit, x, kind="half"):
     check(_L().dfu_v32_vit_assemble(_p(po), _p(vit.cls_token.detach()), _p(vit.pos_embed.detach()), _p(tok), B, T, D, _st()),
           "v32_vit_assemble")
     ops._count()
+    _q(tok)
     for blk in vit.blocks:
         tok = _attention(_layernorm(tok, blk.norm1), blk.attn, B, T, res=tok)
         h = linear(_layernorm(tok, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=2)
@@ -227,9 +249,18 @@ def vit_fp32(vit, x, kind="half"):
 
 # ------------------------------------------------------------------------------------------------- models
 @torch.no_grad()
-def forward_fp32(model, *inputs):
+def forward_fp32(model, *inputs, emulate_bf16_storage=False):
     """Logits (fp32) of MultimodalFusionModel(rgb, thermal), RGBOnlyModel(rgb), ThermalOnlyModel(thermal), a bare
-    DfuResNet50 or DfuVisionTransformer, computed in fp32 validation mode.  Inputs: uint8 NHWC or fp32 NCHW normalised."""
+    DfuResNet50 or DfuVisionTransformer, computed in fp32 validation mode.  Inputs: uint8 NHWC or fp32 NCHW normalised.
+    emulate_bf16_storage=True keeps the fp32 arithmetic but rounds every stored activation and GEMM weight to bf16."""
+    _EMULATE[0] = bool(emulate_bf16_storage)
+    try:
+        return _forward_fp32(model, *inputs)
+    finally:
+        _EMULATE[0] = False
+
+
+def _forward_fp32(model, *inputs):
     if isinstance(model, MultimodalFusionModel):
         rgb, thermal = inputs
         rf, tf = resnet_fp32(model.resnet, rgb), vit_fp32(model.vit, thermal)

@@ -257,6 +257,22 @@ int dfu_saliency(const float* dimg, float* out, float* max_scratch, int32_t C, i
 int dfu_tta_vote(const float* probs, float* mean_prob, int64_t* pred, int32_t n, int32_t V, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device-side evaluation metrics.  Replaces, per batch, the device->host syncs of the reference loops
+ * (train_multimodal_fusion.py:383-386; extended_metrics.py:636-640) and, per epoch, sklearn's confusion_matrix / precision /
+ * recall / f1 / roc_auc_score / precision_recall_curve + auc / matthews_corrcoef / cohen_kappa_score
+ * (extended_metrics.py:374-446).
+ *   state [6] int64 (caller zeroes): n, tn, fp, fn, tp, loss terms;  loss_acc [1] fp64 (caller zeroes);
+ *   probs / y_true / y_pred [capacity]: softmax(logits)[:,1] (sigmoid for C = 1), label, argmax of every sample seen.
+ *   dfu_metrics_update: one launch per batch, no sync; `loss` (device scalar) may be null.
+ *   dfu_metrics_finalize: out24 (fp64) = tn fp fn tp accuracy precision recall f1 sensitivity specificity ppv npv fpr fnr
+ *   auc_roc auc_pr mcc kappa balanced_accuracy f_harmonic mean_loss n overflowed reserved;  capacity <= 16384.
+ * ------------------------------------------------------------------------------------------- */
+int dfu_metrics_update(const float* logits, const int64_t* labels, const float* loss, int32_t B, int32_t C, int64_t* state,
+                       double* loss_acc, float* probs, int32_t* y_true, int32_t* y_pred, int64_t capacity, void* stream);
+int dfu_metrics_finalize(const int64_t* state, const double* loss_acc, const float* probs, const int32_t* y_true, int64_t capacity,
+                         double* out24, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a9, resize half: transforms.Resize((224,224)) of the reference pipelines (train_multimodal_fusion.py:174,186,195,204;
  * extended_metrics.py:290-300) fused with ToTensor + Normalize.  Replaces torchvision F.resize -> PIL.Image.resize(BILINEAR)
  * (Pillow ImagingResample: antialiased triangle filter, 22-bit fixed-point coefficients, horizontal then vertical pass, each
@@ -298,6 +314,9 @@ int dfu_v32_im2col(const float* x, float* col, int32_t B, int32_t H, int32_t W, 
                    int32_t pad, int32_t Ho, int32_t Wo, void* stream);
 /* timm PatchEmbed unfold of fp32 NHWC [B,224,224,3] -> [B*196, 768], columns ordered (c,i,j). */
 int dfu_v32_patchify(const float* x_nhwc, float* out, int32_t B, void* stream);
+/* x <- float(bf16(x)) in place: emulates bf16 STORAGE of an activation / weight inside the fp32 path (validation.py uses it to
+ * show that the fast path's distance from the fp32 reference is storage rounding, not arithmetic). */
+int dfu_v32_round_bf16(float* x, int64_t n, void* stream);
 int dfu_v32_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t cols, void* stream);
 int dfu_v32_vit_assemble(const float* patch_out, const float* cls, const float* pos, float* tokens, int32_t B, int32_t T, int32_t D,
                          void* stream);

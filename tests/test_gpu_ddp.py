@@ -53,7 +53,7 @@ def _rank_main(rank, world, port, out_dir):
     broadcast_parameters(model)
     opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
     bucketer = GradBucketer(list(model.parameters()))
-    opt.set_grad_source(bucketer.grad_source)
+    opt.set_grad_source(bucketer.grad_source, bucketer)
     ts = TrainStep(model, opt, None, use_graph=False, bucketer=bucketer)
     loss, _ = ts(*_batch(rank, dev))
     torch.cuda.synchronize()
@@ -103,7 +103,7 @@ def test_n_gpu_step_equals_one_gpu_micro_batched_step(world, tmp_path):
     for n, p in params.items():
         bi, off, cnt = bucketer.slot[p]
         bucketer.flat[bi][off:off + cnt].copy_(avg[n])
-    opt.set_grad_source(bucketer.grad_source)
+    opt.set_grad_source(bucketer.grad_source, bucketer)
     opt.step()
     torch.cuda.synchronize()
 

@@ -569,7 +569,8 @@ def test_fused_adamw_state_dict_roundtrips_with_torch_adamw(dev, tmp_path):
     shapes = [(64, 32, 3, 3), (256,), (300, 70), (1, 197, 8)]
 
     def make(channels_last):
-        ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+        g0 = torch.Generator().manual_seed(7)                # every parameter set starts from the same values
+        ps = [torch.nn.Parameter(torch.randn(s, generator=g0).to(dev)) for s in shapes]
         if channels_last:
             ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
         return ps
@@ -758,3 +759,59 @@ def test_folded_conv_batchnorm_matches_conv_then_batchnorm(ops, dev, cfg):
     close(b1, bn.bias - bn.running_mean * bn.weight / torch.sqrt(bn.running_var + bn.eps), 1e-5, 1e-6)
     bn.train(); bn.eval()
     assert conv.__dict__["_dfu_folded"][0] != (None,) and RN._folded(conv, bn)[0].data_ptr() == ptr
+
+
+# ----------------------------------------------------------------------------------------------- device-side metrics
+@pytest.mark.parametrize("n,ties,seed", [(276, False, 0), (276, True, 1), (131, True, 2), (1000, False, 3), (7, False, 4)])
+def test_device_metrics_match_the_reference_sklearn_calculator(dev, n, ties, seed):
+    """dfu_metrics_update / dfu_metrics_finalize against what extended_metrics.py:374-446 computes with sklearn on the host
+    (confusion matrix, precision / recall / F1, ROC-AUC, PR-AUC via precision_recall_curve + auc, MCC, kappa ...), fed in the
+    reference's batches of 8 with the loss of every batch -- no host sync until compute()."""
+    import numpy as np
+    from sklearn.metrics import (accuracy_score, auc, cohen_kappa_score, confusion_matrix, f1_score, matthews_corrcoef,
+                                 precision_recall_curve, precision_score, recall_score, roc_auc_score)
+    from dfu_multimodal_b200.metrics import DeviceMetrics
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(n, 2, generator=g) * 2
+    if ties:
+        logits = (logits * 2).round() / 2                     # many equal scores: thresholds are shared
+    labels = (torch.rand(n, generator=g) < 0.55).long()
+    labels[0], labels[1] = 0, 1
+    losses = torch.rand((n + 7) // 8, generator=g)
+    dm = DeviceMetrics(dev, capacity=1024)
+    dm.reset()
+    for bi, i in enumerate(range(0, n, 8)):
+        dm.update(logits[i:i + 8].to(dev), labels[i:i + 8].to(dev), losses[bi].to(dev))
+    m = dm.compute()
+    y_true = labels.numpy()
+    probs = torch.softmax(logits.to(dev), dim=1)[:, 1].cpu().numpy()       # extended_metrics.py:636
+    y_pred = logits.argmax(1).numpy()
+    yt, yp, pr = dm.samples()
+    assert np.array_equal(yt, y_true) and np.array_equal(yp, y_pred) and np.abs(pr - probs).max() < 1e-6
+    tn, fp, fn, tp = confusion_matrix(y_true, y_pred).ravel()
+    assert (m["tn"], m["fp"], m["fn"], m["tp"], m["n"]) == (tn, fp, fn, tp, n) and not m["overflowed"]
+    precision, recall, _ = precision_recall_curve(y_true, pr)
+    want = {"accuracy": accuracy_score(y_true, y_pred), "precision": precision_score(y_true, y_pred, zero_division=0),
+            "recall": recall_score(y_true, y_pred, zero_division=0), "f1": f1_score(y_true, y_pred, zero_division=0),
+            "auc_roc": roc_auc_score(y_true, pr), "auc_pr": auc(recall, precision), "mcc": matthews_corrcoef(y_true, y_pred),
+            "kappa": cohen_kappa_score(y_true, y_pred), "sensitivity": tp / (tp + fn), "specificity": tn / (tn + fp),
+            "mean_loss": float(losses.double().mean())}
+    for k, v in want.items():
+        assert abs(m[k] - v) < 1e-9 if k != "mean_loss" else abs(m[k] - v) < 1e-6, (k, m[k], v)
+    assert abs(m["balanced_accuracy"] - 0.5 * (want["sensitivity"] + want["specificity"])) < 1e-12
+
+
+def test_device_metrics_sigmoid_head_and_overflow_flag(dev):
+    from dfu_multimodal_b200.metrics import DeviceMetrics
+    dm = DeviceMetrics(dev, capacity=16)
+    logits = torch.tensor([[2.0], [-1.0], [0.5], [-3.0]], device=dev)
+    labels = torch.tensor([1, 0, 0, 1], device=dev)
+    for _ in range(5):
+        dm.update(logits, labels)
+    m = dm.compute()
+    assert m["n"] == 20 and m["overflowed"] and (m["tp"], m["tn"], m["fp"], m["fn"]) == (5, 5, 5, 5)
+    assert m["mean_loss"] != m["mean_loss"]                   # no loss was logged: NaN
+    dm.reset()
+    dm.update(logits, labels)
+    m = dm.compute()
+    assert m["n"] == 4 and not m["overflowed"] and abs(m["auc_roc"] - 0.5) < 1e-12

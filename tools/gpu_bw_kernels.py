@@ -1,5 +1,5 @@
-"""One launch of every bandwidth-bound kernel of the train step at its B=128 size (for `ncu --set full` captures and for a
-quick CUDA-event table).  Usage: python tools/gpu_bw_kernels.py [iters]"""
+"""Every bandwidth-bound kernel of the train step at its B=128 sizes: a CUDA-event table (python tools/gpu_bw_kernels.py
+[iters]) or exactly one launch of each at its largest shape for `ncu --set full` (python tools/gpu_bw_kernels.py ncu)."""
 import os
 import sys
 
@@ -12,12 +12,13 @@ from dfu_multimodal_b200.optim import FusedAdamW  # noqa: E402
 
 dev = torch.device("cuda:0")
 BF = torch.bfloat16
-iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+NCU = len(sys.argv) > 1 and sys.argv[1] == "ncu"          # one launch of each kernel at its largest shape, no warm-up
+iters = 1 if NCU else (int(sys.argv[1]) if len(sys.argv) > 1 else 5)
 PEAK = 6556.0
 
 
 def timeit(fn):
-    for _ in range(2):
+    for _ in range(0 if NCU else 2):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,7 +34,7 @@ def report(name, us, nbytes):
     print("%-52s %9.1f us %8.0f GB/s (%5.1f%% of %d)" % (name, us, nbytes / us / 1e3, nbytes / us / 1e3 / PEAK * 100, PEAK), flush=True)
 
 
-for M, C in ((401408, 256), (401408, 64), (100352, 512), (25088, 1024), (6272, 2048)):
+for M, C in (((401408, 256),) if NCU else ((401408, 256), (401408, 64), (100352, 512), (25088, 1024), (6272, 2048))):
     y = torch.randn(M, C, device=dev).to(BF)
     res = torch.randn(M, C, device=dev).to(BF)
     dz = torch.randn(M, C, device=dev).to(BF)

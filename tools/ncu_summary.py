@@ -48,5 +48,35 @@ def full(path):
                 print("   %-66s %14s %s" % (k, d[k], units[hdr.index(k)]))
 
 
+def traffic(path, kernel_regex, algorithmic_bytes, out="profiles/roofline_traffic.json"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch matching kernel_regex -> the JSON bench.py reads for
+    roofline.traffic.  python tools/ncu_summary.py traffic rep.ncu-rep 'dfu_tc_gemm_kernel' 203.0e6"""
+    import json
+    import re
+    out_csv = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out_csv.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if not re.search(kernel_regex, d.get("Kernel Name", "")):
+            continue
+
+        def gbytes(key):
+            v = float(d[key].replace(",", ""))
+            u = units[hdr.index(key)].lower()
+            return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+        total = gbytes("dram__bytes_read.sum") + gbytes("dram__bytes_write.sum")
+        rec = {"bytes_per_launch": total, "algorithmic_bytes_per_launch": float(algorithmic_bytes), "kernel": d["Kernel Name"][:120],
+               "grid": d.get("Grid Size"), "source": path, "how": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch"}
+        with open(out, "w") as f:
+            json.dump(rec, f, indent=1)
+        print(json.dumps(rec))
+        return
+    raise SystemExit("no kernel matching %r in %s" % (kernel_regex, path))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
