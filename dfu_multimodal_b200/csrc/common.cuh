@@ -39,9 +39,10 @@ int dfu_num_sms();
 // the NEXT kernel of the stream be scheduled as soon as all CTAs of this one are resident (its CTAs take over SMs as this
 // kernel's tail drains and run their prologue), `griddepcontrol.wait` blocks until the PREVIOUS kernel has completed and
 // its writes are visible.  Every kernel waits before its first global-memory access, so the chain of waits keeps the
-// stream's order for data (a kernel that passed its wait implies all earlier kernels have finished).  Saves the launch
-// latency and prologue at each of the ~600 kernel boundaries of a train step (CUDA graphs keep the edges programmatic).
-// DFU_PDL=0 launches without the attribute (the two instructions are then no-ops).
+// stream's order for data (a kernel that passed its wait implies all earlier kernels have finished).  Meant to save the
+// launch latency and prologue at each of the ~600 kernel boundaries of a train step.  MEASURED on B200 (profiles/r02c_*): no
+// gain under CUDA-graph replay (31.76 ms with, 31.51 ms without), so the attribute is only set with DFU_PDL=1; without it
+// the two instructions are no-ops.
 bool dfu_pdl_enabled();
 
 #ifdef __CUDACC__

@@ -304,241 +304,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
     }
 }
 
-// ---- second generation of the three streaming BatchNorm kernels (DFU_BN_V2=0 selects the first).
-// ncu on B200 (profiles/r02b_ncu_full_bandwidth_kernels.txt): the kernels above run at 24 % occupancy (92-128 registers, 2
-// blocks per SM) with ~80 instructions per 16-byte vector and reach 50-62 % of the HBM copy rate.  Here a block streams
-// CONTIGUOUS chunks of 256*U vectors (the channel vector of a thread is still fixed: 256 is a multiple of C/8), with a
-// register budget that lets 3-4 blocks share an SM, and the vector index doubles as the mask index.
-template <int U, int MODE>
-__global__ void __launch_bounds__(256, MODE == 1 ? 3 : 4) bn_reduce2_kernel(const bf16* __restrict__ a, const bf16* __restrict__ y,
-                                                           const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ sums, long long M, int C,
-                                                           int relu, const unsigned char* __restrict__ zmask) {
-    pdl_sync();
-    __shared__ float red[2][256][9];
-    const int cvec = C >> 3;
-    const int cv = threadIdx.x & (cvec - 1);
-    float s1[8], s2[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-    const bool use_bits = MODE == 1 && relu && zmask != nullptr;
-    const bool mask_from_y = MODE == 1 && relu && !use_bits;
-    float xa[8], xb[8], mp[8], mq[8];            // xhat = xa*y + xb;  forward mask (no saved bits): mp*y + mq > 0
-    if (MODE == 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float mean = mean_invstd[cv * 8 + i], invstd = mean_invstd[C + cv * 8 + i];
-            xa[i] = invstd;
-            xb[i] = -mean * invstd;
-            mp[i] = mask_from_y ? gamma[cv * 8 + i] * invstd : 0.f;
-            mq[i] = mask_from_y ? beta[cv * 8 + i] - mean * mp[i] : 1.f;
-        }
-    }
-    const long long nvec = M * cvec;
-    const long long chunk = 256ll * U;
-    for (long long base = (long long)blockIdx.x * chunk + threadIdx.x; base < nvec; base += (long long)gridDim.x * chunk) {
-        bf16x8 va[U], vy[U];
-        unsigned int mb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long v = base + u * 256;
-            if (v < nvec) {
-                va[u] = ld8(a + v * 8);
-                if (MODE == 1) {
-                    vy[u] = ld8(y + v * 8);
-                    if (use_bits) mb[u] = zmask[v];
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (base + u * 256 >= nvec) break;
-            float f[8];
-            unpack8(va[u], f);
-            if (MODE == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
-            } else {
-                float yy[8];
-                unpack8(vy[u], yy);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float xh = fmaf(xa[i], yy[i], xb[i]);
-                    bool keep = true;
-                    if (use_bits) keep = (mb[u] >> i) & 1u;
-                    else if (mask_from_y) keep = fmaf(yy[i], mp[i], mq[i]) > 0.f;      // the forward kernel's own expression
-                    const float d = keep ? f[i] : 0.f;
-                    s1[i] += d;
-                    s2[i] = fmaf(d, xh, s2[i]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s1[i]; red[1][threadIdx.x][i] = s2[i]; }
-    __syncthreads();
-    const int lanes = 256 / cvec;
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const int v = c >> 3, i = c & 7;
-        float t1 = 0.f, t2 = 0.f;
-        for (int k = 0; k < lanes; ++k) { t1 += red[0][k * cvec + v][i]; t2 += red[1][k * cvec + v][i]; }
-        atomicAdd(sums + c, t1);
-        atomicAdd(sums + C + c, t2);
-    }
-}
-
-template <int U>
-__global__ void __launch_bounds__(256, 3) bn_apply2_kernel(const bf16* __restrict__ y, float* __restrict__ mean_invstd,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const bf16* __restrict__ res, bf16* __restrict__ z, long long M, int C, int relu,
-                                                          const float* __restrict__ sums, float* __restrict__ running_mean,
-                                                          float* __restrict__ running_var, long long* __restrict__ nbt, float eps,
-                                                          float momentum, unsigned char* __restrict__ zmask) {
-    pdl_sync();
-    const int cvec = C >> 3;
-    const int cv = threadIdx.x & (cvec - 1);
-    float sc[8], sh[8];
-    if (sums) {
-        const float inv_m = 1.f / (float)M;
-        if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = cv * 8 + i;
-            const float mean = sums[c] * inv_m;
-            const float var = fmaxf(sums[C + c] * inv_m - mean * mean, 0.f);
-            const float invstd = rsqrtf(var + eps);
-            if (blockIdx.x == 0 && threadIdx.x < cvec) {
-                mean_invstd[c] = mean;
-                mean_invstd[C + c] = invstd;
-                if (running_mean) {
-                    const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
-                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-                }
-            }
-            sc[i] = gamma[c] * invstd;
-            sh[i] = beta[c] - mean * sc[i];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = cv * 8 + i;
-            sc[i] = gamma[c] * mean_invstd[C + c];
-            sh[i] = beta[c] - mean_invstd[c] * sc[i];
-        }
-    }
-    const long long nvec = M * cvec;
-    const long long chunk = 256ll * U;
-    for (long long base = (long long)blockIdx.x * chunk + threadIdx.x; base < nvec; base += (long long)gridDim.x * chunk) {
-        bf16x8 vy[U], vr[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long v = base + u * 256;
-            if (v < nvec) {
-                vy[u] = ld8(y + v * 8);
-                if (res) vr[u] = ld8(res + v * 8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long v = base + u * 256;
-            if (v >= nvec) break;
-            float f[8];
-            unpack8(vy[u], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
-            if (res) {
-                float rr[8];
-                unpack8(vr[u], rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += rr[i];
-            }
-            if (relu) {
-                if (zmask) {
-                    unsigned int bits = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bits |= (f[i] > 0.f ? 1u : 0u) << i;
-                    zmask[v] = (unsigned char)bits;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            st8(z + v * 8, pack8(f));
-        }
-    }
-}
-
-template <int U>
-__global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
-                                                              const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, const float* __restrict__ sums,
-                                                              bf16* __restrict__ dy, bf16* __restrict__ dres, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, long long M, int C, int relu, int train,
-                                                              const unsigned char* __restrict__ zmask) {
-    pdl_sync();
-    const int cvec = C >> 3;
-    const int cv = threadIdx.x & (cvec - 1);
-    // dy = ca*d + cb*y + cc with d = dz masked; mask without saved bits: cp*y + cq > 0
-    float ca[8], cb[8], cc[8], cq[8];
-    const float inv_m = 1.f / (float)M;
-    const bool use_bits = relu && zmask != nullptr;
-    const bool mask_from_y = relu && !use_bits;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = cv * 8 + i;
-        const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
-        const float g = gamma[c] * invstd;
-        const float k1 = train ? sums[c] * inv_m : 0.f;
-        const float k2 = train ? sums[C + c] * inv_m : 0.f;
-        ca[i] = g;                                   // also the forward pass's scale: mask = ca*y + cq > 0
-        cb[i] = -g * k2 * invstd;
-        cc[i] = g * (k2 * invstd * mean - k1);
-        cq[i] = mask_from_y ? beta[c] - mean * g : 1.f;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < cvec && dgamma) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dbeta[cv * 8 + i] = sums[cv * 8 + i];
-            dgamma[cv * 8 + i] = sums[C + cv * 8 + i];
-        }
-    }
-    const long long nvec = M * cvec;
-    const long long chunk = 256ll * U;
-    for (long long base = (long long)blockIdx.x * chunk + threadIdx.x; base < nvec; base += (long long)gridDim.x * chunk) {
-        bf16x8 vd[U], vy[U];
-        unsigned int mb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long v = base + u * 256;
-            if (v < nvec) {
-                vd[u] = ld8(dz + v * 8);
-                vy[u] = ld8(y + v * 8);
-                if (use_bits) mb[u] = zmask[v];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long v = base + u * 256;
-            if (v >= nvec) break;
-            float d[8], yy[8];
-            unpack8(vd[u], d);
-            unpack8(vy[u], yy);
-            if (use_bits) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (!((mb[u] >> i) & 1u)) d[i] = 0.f;
-            } else if (mask_from_y) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (!(fmaf(yy[i], ca[i], cq[i]) > 0.f)) d[i] = 0.f;
-            }
-            if (dres) st8(dres + v * 8, pack8(d));
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaf(ca[i], d[i], fmaf(cb[i], yy[i], cc[i]));
-            st8(dy + v * 8, pack8(o));
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row, D <= 1024, D % 8 == 0: row kept in registers (<= 4 vectors of 8 per lane).
 constexpr int LN_MAXV = 4;
@@ -787,10 +552,7 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __res
 }
 
 bool bn_shape_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0; }
-// DFU_BN_V2=0: first-generation kernels
-const bool g_bn_v2 = []() { const char* e = getenv("DFU_BN_V2"); return !(e && e[0] == '0'); }();
-// grid of the chunked kernels: enough blocks for `per_sm` resident ones, each walking contiguous chunks of 256*U vectors
-inline int bn2_grid(long long M, int C, int U, int per_sm) { return grid_cap((M * (C / 8) + 256ll * U - 1) / (256ll * U), per_sm); }
+
 
 // Eval-mode BatchNorm folded into the preceding convolution's weights: one block per output channel.
 __global__ void __launch_bounds__(128) fold_bn_weights_kernel(const float* __restrict__ w, int K, const float* __restrict__ gamma,
@@ -813,9 +575,6 @@ extern "C" int dfu_bn_stats(const void* y, float* sums, int64_t M, int32_t C, vo
     const int rpi = 256 / (C / 8);
     // every block ends with 2C global atomics: one resident wave (launch bounds: 2 blocks per SM) keeps them at
     // 296 x 2C -- with 8 blocks per SM the atomics of the wide, short layers (C >= 512) cost more than their loads
-    if (g_bn_v2)
-        dfu_launch(bn_reduce2_kernel<4, 0>, bn2_grid(M, C, 4, 4), 256, 0, (cudaStream_t)stream, (const bf16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0, nullptr);
-    else
     dfu_launch(bn_reduce_kernel<0>, grid_cap((M + rpi - 1) / rpi, 2), 256, 0, (cudaStream_t)stream, (const bf16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0, nullptr);
     DFU_CHECK_LAUNCH("bn_stats");
     return DFU_OK;
@@ -840,10 +599,6 @@ extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float
     DFU_CHECK_ARG(y && mean_invstd && gamma && beta && z && M > 0 && bn_shape_ok(C), "dfu_bn_apply: unsupported shape M=%lld C=%d",
                   (long long)M, C);
     const int rpi = 256 / (C / 8);
-    if (g_bn_v2)
-        dfu_launch(bn_apply2_kernel<4>, bn2_grid(M, C, 4, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu,
-                   nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, zmask);
-    else
     dfu_launch(bn_apply_kernel, grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, nullptr, nullptr,
         nullptr, nullptr, 0.f, 0.f, zmask);
     DFU_CHECK_LAUNCH("bn_apply");
@@ -856,10 +611,6 @@ extern "C" int dfu_bn_apply_train(const void* y, const float* sums, const float*
                   "dfu_bn_apply_train: unsupported shape M=%lld C=%d", (long long)M, C);
     DFU_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "dfu_bn_apply_train: running_mean/var go together");
     const int rpi = 256 / (C / 8);
-    if (g_bn_v2)
-        dfu_launch(bn_apply2_kernel<4>, bn2_grid(M, C, 4, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, sums, running_mean,
-                   running_var, (long long*)num_batches_tracked, eps, momentum, zmask);
-    else
     dfu_launch(bn_apply_kernel, grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, sums, running_mean, running_var,
         (long long*)num_batches_tracked, eps, momentum, zmask);
     DFU_CHECK_LAUNCH("bn_apply_train");
@@ -871,9 +622,6 @@ extern "C" int dfu_bn_bwd_reduce(const void* dz, const void* z, const uint8_t* z
     DFU_CHECK_ARG(dz && y && mean_invstd && sums && M > 0 && bn_shape_ok(C) && (!relu || z || zmask || (gamma && beta)),
                   "dfu_bn_bwd_reduce: bad args");
     const int rpi = 256 / (C / 8);
-    if (g_bn_v2 && !(relu && z && !zmask))        // (a saved z as the mask source is a first-generation feature)
-        dfu_launch(bn_reduce2_kernel<2, 1>, bn2_grid(M, C, 2, 3), 256, 0, (cudaStream_t)stream, (const bf16*)dz, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu, zmask);
-    else
     dfu_launch(bn_reduce_kernel<1>, grid_cap((M + rpi - 1) / rpi, 2), 256, 0, (cudaStream_t)stream, (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, M, C, relu, zmask);
     DFU_CHECK_LAUNCH("bn_bwd_reduce");
     return DFU_OK;
@@ -884,10 +632,6 @@ extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const uint8_t* zm
     DFU_CHECK_ARG(dz && y && mean_invstd && gamma && sums && dy && M > 0 && bn_shape_ok(C) && (!relu || z || zmask || beta),
                   "dfu_bn_bwd_apply: bad args");
     const int rpi = 256 / (C / 8);
-    if (g_bn_v2 && !(relu && z && !zmask))
-        dfu_launch(bn_bwd_apply2_kernel<2>, bn2_grid(M, C, 2, 6), 256, 0, (cudaStream_t)stream, (const bf16*)dz, (const bf16*)y, mean_invstd, gamma, beta, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta,
-                   M, C, relu, train, zmask);
-    else
     dfu_launch(bn_bwd_apply_kernel, grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream, (const bf16*)dz, (const bf16*)z, (const bf16*)y, mean_invstd, gamma, beta, sums, (bf16*)dy, (bf16*)dres, dgamma, dbeta,
         M, C, relu, train, zmask);
     DFU_CHECK_LAUNCH("bn_bwd_apply");

@@ -15,7 +15,11 @@ CHUNK = 65536
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # the extra keys are torch.optim.AdamW's own group entries with the values this class implements: a state_dict saved
+        # here must make a stock AdamW behave as AdamW when it loads it (a group without `decoupled_weight_decay` is read as
+        # plain Adam with L2 decay by torch >= 2.7)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
         super().__init__(params, defaults)
         self._tables = {}      # (group index, pointer signature) -> cached device table
         self._grad_source = None
@@ -147,6 +151,8 @@ class FusedAdamW(torch.optim.Optimizer):
         ticked = set()         # the shared counter advances once per step() however many groups read it
         ops.PARAM_EPOCH[0] += 1        # parameters change below without torch's version counters noticing (folded-BN caches)
         for gi, group in enumerate(self.param_groups):
+            if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay", True) is False:
+                raise RuntimeError("FusedAdamW implements AdamW as the reference configures it: no amsgrad / maximize, decoupled weight decay")
             params, grads = [], []
             g_bf16, scale = False, 1.0
             for p in group["params"]:

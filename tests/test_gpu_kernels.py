@@ -628,9 +628,15 @@ def test_fused_adamw_state_dict_roundtrips_with_torch_adamw(dev, tmp_path):
     # (c) and a stock AdamW can resume from a FusedAdamW checkpoint
     d = [torch.nn.Parameter(p.detach().clone()) for p in c]
     od = torch.optim.AdamW(d, lr=1e-3, weight_decay=1e-2)
-    od.load_state_dict(oc.state_dict())
+    torch.save(oc.state_dict(), tmp_path / "fused2.pt")       # (a state_dict holds REFERENCES to the live moments: go through a file)
+    od.load_state_dict(torch.load(tmp_path / "fused2.pt", map_location="cpu"))
     run(od, d, [7])
     run(oc, c, [7])
+    truth7 = make(False)
+    run(torch.optim.AdamW(truth7, lr=1e-3, weight_decay=1e-2), truth7, range(8))
+    print("resume into stock AdamW: max|fused - stock| per parameter", [float((p - q).abs().max()) for p, q in zip(c, d)],
+          "| max|fused - uninterrupted|", [float((p - q).abs().max()) for p, q in zip(c, truth7)],
+          "| max|stock - uninterrupted|", [float((p - q).abs().max()) for p, q in zip(d, truth7)])
     for p, q in zip(c, d):
         close(p, q, 1e-5, 1e-6)
 
