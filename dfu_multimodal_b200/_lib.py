@@ -52,6 +52,12 @@ class V32GemmArgs(ctypes.Structure):
     ]
 
 
+class AugmentParams(ctypes.Structure):
+    _fields_ = [("flags", ctypes.c_int32), ("rot_kind", ctypes.c_int32), ("rot", ctypes.c_int32 * 6), ("aff_kind", ctypes.c_int32),
+                ("aff", ctypes.c_int32 * 6), ("n_color", ctypes.c_int32), ("color_op", ctypes.c_int32 * 3), ("color_f", ctypes.c_float * 3),
+                ("aff_xtab", ctypes.c_int16 * 224), ("aff_ytab", ctypes.c_int16 * 224)]
+
+
 class AdamWTensor(ctypes.Structure):
     _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("shadow", ctypes.c_void_p), ("numel", ctypes.c_int64)]

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdfu_b200.so")
 STAMP = os.path.join(HERE, ".libdfu_b200.stamp")
 
-SOURCES = ["api.cu", "tc_gemm.cu", "layout.cu", "norm.cu", "pointwise.cu", "train_misc.cu", "attention.cu", "validate_f32.cu", "resize.cu", "metrics.cu"]
+SOURCES = ["api.cu", "tc_gemm.cu", "layout.cu", "norm.cu", "pointwise.cu", "train_misc.cu", "attention.cu", "validate_f32.cu", "resize.cu", "metrics.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

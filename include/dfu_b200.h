@@ -273,6 +273,33 @@ int dfu_metrics_finalize(const int64_t* state, const double* loss_acc, const flo
                          double* out24, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Train-time augmentation on the device, fused with ToTensor + Normalize: replaces the PIL pipeline
+ * RandomHorizontalFlip -> RandomVerticalFlip -> RandomRotation(30) -> [ColorJitter] -> [RandomAffine] of
+ * train_multimodal_fusion.py:173-199 (torchvision.transforms.functional hflip / vflip / rotate / adjust_brightness /
+ * adjust_contrast / adjust_saturation / affine on PIL images).  The HOST draws the parameters and prepares, per image, the
+ * inverse maps exactly as torchvision + Pillow do (dfu_multimodal_b200/augment.py); given them the output is bit-identical.
+ *   flags: bit 0 horizontal flip, bit 1 vertical flip.
+ *   rot_kind / aff_kind: 0 identity, 1 Pillow affine_fixed with the six 16.16 coefficients in rot[] / aff[], 2 / 3 / 4 rotation by
+ *   180 / 90 / 270 degrees (Pillow's transpose fast paths), 5 (aff only) Pillow ImagingScaleAffine lookup tables aff_xtab / aff_ytab.
+ *   color_op[k] in application order: 0 brightness, 1 contrast, 2 saturation, factor color_f[k]; n_color of them.
+ *   src [B,H,W,3] uint8 (H, W <= 224); luma_sums [B] uint64 scratch; out_mode as dfu_resize_u8 (0 uint8 / 1 bf16 NHWC / 2 patches).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t flags;
+    int32_t rot_kind;
+    int32_t rot[6];
+    int32_t aff_kind;
+    int32_t aff[6];
+    int32_t n_color;
+    int32_t color_op[3];
+    float color_f[3];
+    int16_t aff_xtab[224];
+    int16_t aff_ytab[224];
+} dfu_augment_params;
+int dfu_augment_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, const dfu_augment_params* params, uint64_t* luma_sums,
+                   int32_t out_mode, void* out, const float* mean3_host, const float* std3_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a9, resize half: transforms.Resize((224,224)) of the reference pipelines (train_multimodal_fusion.py:174,186,195,204;
  * extended_metrics.py:290-300) fused with ToTensor + Normalize.  Replaces torchvision F.resize -> PIL.Image.resize(BILINEAR)
  * (Pillow ImagingResample: antialiased triangle filter, 22-bit fixed-point coefficients, horizontal then vertical pass, each

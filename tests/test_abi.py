@@ -76,3 +76,13 @@ def test_argument_validation_needs_no_device():
     assert lib.dfu_gemm(None, None) != 0
     assert b"null" in lib.dfu_last_error()
     assert lib.dfu_relu(None, None, 0, None) != 0
+
+
+def test_augment_params_struct_matches_header_layout():
+    import re
+    with open(_lib.HEADER) as f:
+        text = f.read()
+    body = re.search(r"typedef struct \{([^}]*)\} dfu_augment_params;", text, flags=re.S).group(1)
+    names = [re.sub(r"\[.*", "", d.strip().split()[-1]) for d in body.split(";") if d.strip()]
+    assert names == [f[0] for f in _lib.AugmentParams._fields_]
+    assert ctypes.sizeof(_lib.AugmentParams) == 4 * (2 + 6 + 1 + 6 + 1 + 3 + 3) + 2 * 224 * 2

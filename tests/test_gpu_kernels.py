@@ -821,3 +821,37 @@ def test_device_metrics_sigmoid_head_and_overflow_flag(dev):
     dm.update(logits, labels)
     m = dm.compute()
     assert m["n"] == 4 and not m["overflowed"] and abs(m["auc_roc"] - 0.5) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------- f1: train-time augmentation
+def test_gpu_augmentation_is_bit_identical_to_the_reference_pipeline(ops, dev):
+    """dfu_augment_u8 against the numpy restatement of the reference's PIL pipeline (itself pinned to torchvision on the CPU):
+    flips, RandomRotation, ColorJitter in drawn order, RandomAffine -- 64 drawn parameter sets plus Pillow's fast paths --
+    uint8 output EQUAL; then the fused Normalize (+ patch unfold) against the exact preprocessing kernels."""
+    import random
+    import numpy as np
+    from dfu_multimodal_b200 import augment as G
+    from oracle import augment_pil as A
+    rng = np.random.RandomState(5)
+    random.seed(5)
+    params = G.draw_params(64, "rgb", rng=random)
+    params += [dict(hflip=False, vflip=False, angle=0.0, affine=dict(angle=0.0, translate=(3, -4), scale=1.1)),
+               dict(hflip=True, vflip=False, angle=180.0), dict(hflip=False, vflip=True, angle=90.0),
+               dict(hflip=True, vflip=True, angle=270.0), dict(hflip=False, vflip=False, angle=0.0),
+               dict(hflip=False, vflip=False, angle=29.5, jitter=dict(order=[1], contrast=0.7, brightness=1.0, saturation=1.0)),
+               dict(hflip=False, vflip=False, angle=-3.0, jitter=dict(order=[2, 1, 0], contrast=1.3, brightness=1.3, saturation=0.7))]
+    B = len(params)
+    imgs = rng.randint(0, 256, (B, 224, 224, 3)).astype(np.uint8)
+    x = torch.from_numpy(imgs).to(dev)
+    got = G.augment_u8(x, params, "u8").cpu().numpy()
+    for i, p in enumerate(params):
+        ref = A.augment(imgs[i], p)
+        assert np.array_equal(got[i], ref), (i, p, int(np.abs(got[i].astype(int) - ref.astype(int)).max()), int((got[i] != ref).sum()))
+    g = torch.from_numpy(got).to(dev)
+    assert torch.equal(G.augment_u8(x, params, "nhwc", "imagenet"), ops.preprocess_u8_nhwc(g, "imagenet"))
+    assert torch.equal(G.augment_u8(x, params, "patches", "half"), ops.preprocess_u8_patches(g, "half"))
+    # thermal draws never contain ColorJitter; the distributions are the reference's
+    tp = G.draw_params(2000, "thermal", rng=random)
+    assert not any("jitter" in p for p in tp)
+    assert 0.55 < sum("affine" in p for p in tp) / 2000 < 0.65 and 0.45 < sum(p["hflip"] for p in tp) / 2000 < 0.55
+    assert all(-30 <= p["angle"] <= 30 for p in tp)

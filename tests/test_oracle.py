@@ -104,3 +104,46 @@ def test_resize_restatement_is_bit_identical_to_pillow():
         assert np.array_equal(resize_bilinear_u8(img), ref), (h, w)
     b, c, k = precompute_coeffs(448, 224)
     assert k == 5 and int(c.sum(1).min()) >= (1 << 22) - 4 and int(c.sum(1).max()) <= (1 << 22) + 4
+
+
+def test_augmentation_restatement_is_bit_identical_to_torchvision_on_pil():
+    """oracle/augment_pil.py against the calls the reference's train transforms make (train_multimodal_fusion.py:173-199):
+    torchvision.transforms.functional hflip / vflip / rotate / adjust_brightness / adjust_contrast / adjust_saturation / affine
+    on PIL images, with the same drawn parameters -- including Pillow's fast paths (right angles, scale-only affine)."""
+    import random
+    import numpy as np
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from oracle import augment_pil as A
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (224, 224, 3)).astype(np.uint8)
+    pil = Image.fromarray(img)
+    random.seed(11)
+    cases = []
+    for _ in range(12):
+        p = dict(hflip=random.random() < 0.5, vflip=random.random() < 0.5, angle=random.uniform(-30, 30))
+        if random.random() < 0.7:
+            order = [0, 1, 2]
+            random.shuffle(order)
+            p["jitter"] = dict(order=order, brightness=random.uniform(0.7, 1.3), contrast=random.uniform(0.7, 1.3),
+                               saturation=random.uniform(0.7, 1.3))
+        if random.random() < 0.7:
+            p["affine"] = dict(angle=random.uniform(-20, 20), scale=random.uniform(0.8, 1.2),
+                               translate=(int(round(random.uniform(-22.4, 22.4))), int(round(random.uniform(-22.4, 22.4)))))
+        cases.append(p)
+    cases += [dict(hflip=False, vflip=False, angle=0.0, affine=dict(angle=0.0, translate=(3, -4), scale=1.1)),
+              dict(hflip=True, vflip=False, angle=180.0), dict(hflip=False, vflip=True, angle=90.0), dict(hflip=True, vflip=True, angle=270.0)]
+    for p in cases:
+        x = pil
+        if p["hflip"]:
+            x = TF.hflip(x)
+        if p["vflip"]:
+            x = TF.vflip(x)
+        x = TF.rotate(x, p["angle"])
+        if "jitter" in p:
+            for op in p["jitter"]["order"]:
+                x = [TF.adjust_brightness, TF.adjust_contrast, TF.adjust_saturation][op](x, p["jitter"][["brightness", "contrast", "saturation"][op]])
+        if "affine" in p:
+            a = p["affine"]
+            x = TF.affine(x, a["angle"], list(a["translate"]), a["scale"], [0.0, 0.0])
+        assert np.array_equal(np.asarray(x), A.augment(img, p)), p
