@@ -19,34 +19,36 @@ struct Norm3 {
 };
 
 // ------------------------------------------------------------------ a9: u8 HWC -> normalised bf16 NHWC
-// 16 pixels-channels (16 bytes) per thread-iteration; 48 bytes = 16 pixels is the channel period, so each
-// thread handles 48 bytes (three 16-byte loads) -> 48 bf16 (six 16-byte stores).
+// Thread t converts the 16 bytes [16 t, 16 t + 16): one 128-bit load, two 128-bit stores, consecutive threads on consecutive
+// addresses in both directions.  16 = 1 (mod 3), so byte j of the thread is channel (t + j) mod 3: the three possible
+// (scale, shift) sequences of a thread are rotations of one another and are picked by t mod 3 once per thread.
+// (The first version gave each thread 48 bytes -- three loads 48 bytes apart, six stores 96 bytes apart -- and ran at 16 %
+// of the HBM copy rate: profiles/r02b_ncu_full_bandwidth_kernels.txt.)
 __global__ void __launch_bounds__(256) preprocess_u8_nhwc_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out,
-                                                                long long n_groups, long long n_bytes, Norm3 nm) {
+                                                                long long n_vec, long long n_bytes, Norm3 nm) {
     pdl_sync();
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_groups;
-         g += (long long)gridDim.x * blockDim.x) {
-        const long long base = g * 48;
-        if (base + 48 <= n_bytes) {
-            uint4 raw[3];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec; t += (long long)gridDim.x * blockDim.x) {
+        const long long base = t * 16;
+        const int c0 = (int)(t % 3);
+        // channel of byte j is (c0 + j) % 3
+        const float s0 = nm.scale[c0], s1 = nm.scale[(c0 + 1) % 3], s2 = nm.scale[(c0 + 2) % 3];
+        const float h0 = nm.shift[c0], h1 = nm.shift[(c0 + 1) % 3], h2 = nm.shift[(c0 + 2) % 3];
+        if (base + 16 <= n_bytes) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + base));
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            float f[16];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) raw[i] = __ldg(reinterpret_cast<const uint4*>(in + base) + i);
-            const uint8_t* b = reinterpret_cast<const uint8_t*>(raw);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int idx = i * 8 + j;
-                    const int c = idx % 3;
-                    f[j] = (float)b[idx] * nm.scale[c] + nm.shift[c];
-                }
-                st8(out + base + i * 8, pack8(f));
+            for (int j = 0; j < 16; ++j) {
+                const float v = (float)((w[j >> 2] >> ((j & 3) * 8)) & 0xffu);
+                const int r = j % 3;
+                f[j] = r == 0 ? fmaf(v, s0, h0) : (r == 1 ? fmaf(v, s1, h1) : fmaf(v, s2, h2));
             }
+            st8(out + base, pack8(f));
+            st8(out + base + 8, pack8(f + 8));
         } else {
             for (long long i = base; i < n_bytes; ++i) {
                 const int c = (int)(i % 3);
-                out[i] = __float2bfloat16((float)in[i] * nm.scale[c] + nm.shift[c]);
+                out[i] = __float2bfloat16(fmaf((float)in[i], nm.scale[c], nm.shift[c]));
             }
         }
     }
@@ -438,8 +440,8 @@ extern "C" int dfu_preprocess_u8_nhwc(const uint8_t* in, void* out, int64_t n_pi
     DFU_CHECK_ARG(in && out && n_pixels > 0 && mean3_host && std3_host, "dfu_preprocess_u8_nhwc: bad args");
     DFU_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dfu_preprocess_u8_nhwc: unaligned buffers");
     const long long n_bytes = n_pixels * 3;
-    const long long groups = (n_bytes + 47) / 48;
-    dfu_launch(preprocess_u8_nhwc_kernel, grid_for(groups, 256), 256, 0, (cudaStream_t)stream, in, (bf16*)out, groups, n_bytes, make_norm(mean3_host, std3_host));
+    const long long n_vec = (n_bytes + 15) / 16;
+    dfu_launch(preprocess_u8_nhwc_kernel, grid_for(n_vec, 256, 16), 256, 0, (cudaStream_t)stream, in, (bf16*)out, n_vec, n_bytes, make_norm(mean3_host, std3_host));
     DFU_CHECK_LAUNCH("preprocess_u8_nhwc");
     return DFU_OK;
 }

@@ -333,7 +333,7 @@ def preprocess_u8_patches(img_u8, kind="half"):
     return out
 
 
-def resize_u8(img_u8, out_hw=(224, 224), mode="u8", kind="imagenet"):
+def resize_u8(img_u8, out_hw=(224, 224), mode="u8", kind="imagenet", out=None):
     """transforms.Resize(out_hw) of a uint8 [B,Hs,Ws,3] batch, bit-identical to torchvision / Pillow BILINEAR (a9).
     mode "u8": the resized uint8 images [B,OH,OW,3]; "nhwc": + ToTensor + Normalize(kind) as bf16 (logical (B,3,OH,OW), NHWC
     memory); "patches": + Normalize + ViT patch unfold -> bf16 [B*196, 768]."""
@@ -348,9 +348,12 @@ def resize_u8(img_u8, out_hw=(224, 224), mode="u8", kind="imagenet"):
     ws = torch.empty(n_ws, dtype=torch.int32, device=img_u8.device)
     code = {"u8": 0, "nhwc": 1, "patches": 2}[mode]
     if code == 0:
-        out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=img_u8.device)
+        if out is None:
+            out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=img_u8.device)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (B, OH, OW, 3) and out.is_contiguous()
         mean = std = None
     else:
+        assert out is None, "a preallocated output is supported for mode 'u8'"
         out = (torch.empty((B, OH, OW, 3), dtype=BF16, device=img_u8.device) if code == 1 else
                torch.empty((B * 196, 768), dtype=BF16, device=img_u8.device))
         mean, std = _norm_consts(kind)
