@@ -73,8 +73,10 @@ class TrainStep:
         self.model.train()
         if len(args) < 2:
             raise RuntimeError("TrainStep: expected (*model_inputs, labels)")
-        if any(t.shape[0] != args[-1].shape[0] for t in args):
-            raise RuntimeError("TrainStep: batch sizes differ: %s" % ([int(t.shape[0]) for t in args],))
+        B = args[-1].shape[0]
+        # image batches are (B, ...) 4-D tensors; an already unfolded ViT patch matrix is [B*196, 768]
+        if any((t.shape[0] != B) if t.dim() != 2 else (t.shape[0] not in (B, B * 196)) for t in args):
+            raise RuntimeError("TrainStep: batch sizes differ: %s" % ([tuple(t.shape) for t in args],))
         if not self.use_graph:
             self.graph = None
             return self._eager(*args)
@@ -117,8 +119,9 @@ class EvalStep:
     def __call__(self, *inputs):
         """step(rgb, thermal) or step(images): (logits [B,C] fp32, softmax[:,1] [B] fp32, argmax [B] int64), on the device."""
         self.model.eval()
-        if any(t.shape[0] != inputs[0].shape[0] for t in inputs):
-            raise RuntimeError("EvalStep: batch sizes differ: %s" % ([int(t.shape[0]) for t in inputs],))
+        B = inputs[0].shape[0]
+        if any((t.shape[0] != B) if t.dim() != 2 else (t.shape[0] not in (B, B * 196)) for t in inputs):
+            raise RuntimeError("EvalStep: batch sizes differ: %s" % ([tuple(t.shape) for t in inputs],))
         refresh_folded(self.model)       # folded conv/BatchNorm weights are inputs of the captured graphs, not part of them
         key = TrainStep._key(*inputs)
         entry = self.graphs.get(key) if self.use_graph else None
