@@ -1,6 +1,7 @@
 // BatchNorm2d (training + eval, forward + backward) over NHWC bf16 [M, C] matrices, LayerNorm over rows,
 // and row softmax.  All are HBM-bound: 128-bit accesses along C / D, fp32 statistics, warp-shuffle reductions.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/dfu_b200.h"
 #include <stdlib.h>
 
@@ -304,6 +305,160 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------ streaming variants
+// ncu on the kernels above (profiles/r02b_ncu_full_bandwidth_kernels.txt): 24 % occupancy, issue slots a third busy, DRAM at
+// 50-62 %: they are bound by the bytes a block can keep in flight out of its registers.  The streaming variants take the
+// loads out of the register file: each block walks a CONTIGUOUS range of 4 KB chunks (256 vectors of 8 channels: the channel
+// vector of a thread stays fixed, 256 being a multiple of C/8) and one thread keeps ST_DEPTH chunks per input tensor in
+// flight with cp.async.bulk into a shared-memory ring (mbarrier transaction counts); the 256 threads consume a chunk with
+// one ld.shared.v4 each.  In flight per SM: blocks x ST_DEPTH x 4 KB per tensor, independent of registers.
+// Measured (profiles/r02k_bn_stream_sweep.txt, r02l_kernel_breakdown_*): bn_apply 20-30 % faster at every layer size (1.85 -> 1.49 ms
+// per step).  The same ring under the two BACKWARD kernels was slower in the step (reduce 1.45 -> 2.11 ms, apply 2.26 -> 2.45 ms:
+// their per-chunk arithmetic no longer overlaps the loads at 2-3 blocks per SM) and was taken out again.
+constexpr int ST_DEPTH = 6;
+constexpr int ST_CHUNK = 256 * 16;           // bytes of one tensor chunk
+
+__device__ __forceinline__ bf16x8 lds8(const void* p) {
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(tc::smem_u32(p)));
+    return *reinterpret_cast<bf16x8*>(&u);
+}
+
+// NT: number of streamed input tensors (1: y; 2: y + res, or dz + y).  issue(chunk, slot) is called by thread 0.
+template <int NT>
+struct StreamRing {
+    uint8_t* smem;                // [ST_DEPTH][NT][ST_CHUNK]
+    uint64_t* full;               // [ST_DEPTH]
+    const uint8_t* src[NT];
+    long long nvec, c_first, c_step, c_count;      // this block's chunks: c_first + i * c_step, i < c_count
+    __device__ __forceinline__ long long chunk(long long i) const { return c_first + i * c_step; }
+    // interleaved = 1: at any moment the blocks read neighbouring chunks (a front moving through the tensor);
+    // interleaved = 0: every block owns one contiguous range
+    __device__ __forceinline__ void plan(long long nvec_, int interleaved) {
+        nvec = nvec_;
+        const long long nchunks = (nvec + 255) / 256;
+        if (interleaved) {
+            c_first = blockIdx.x;
+            c_step = gridDim.x;
+            c_count = nchunks > (long long)blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        } else {
+            const long long per = (nchunks + gridDim.x - 1) / gridDim.x;
+            c_first = min(nchunks, per * blockIdx.x);
+            c_step = 1;
+            c_count = min(nchunks, c_first + per) - c_first;
+        }
+    }
+    __device__ __forceinline__ void issue(long long c, int slot) {
+        const long long v0 = c * 256;
+        const uint32_t bytes = (uint32_t)(min(256ll, nvec - v0) * 16);
+        tc::mbar_expect_tx(&full[slot], bytes * NT);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) tc::bulk_load_1d(smem + ((size_t)slot * NT + t) * ST_CHUNK, src[t] + v0 * 16, bytes, &full[slot]);
+    }
+    __device__ __forceinline__ void start() {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < ST_DEPTH; ++s) tc::mbar_init(&full[s], 1);
+            tc::fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int s = 0; s < ST_DEPTH && s < c_count; ++s) issue(chunk(s), s);
+    }
+    // data of chunk number i (0-based within this block's range) for this thread, tensor t
+    __device__ __forceinline__ const void* slot_ptr(long long i, int t) const {
+        return smem + ((size_t)(i % ST_DEPTH) * NT + t) * ST_CHUNK + threadIdx.x * 16;
+    }
+    __device__ __forceinline__ void wait(long long i) { tc::mbar_wait(&full[i % ST_DEPTH], (uint32_t)((i / ST_DEPTH) & 1)); }
+    // all threads have read chunk i out of shared memory: its slot takes chunk i + ST_DEPTH
+    __device__ __forceinline__ void release(long long i) {
+        __syncthreads();
+        if (threadIdx.x == 0 && i + ST_DEPTH < c_count) issue(chunk(i + ST_DEPTH), (int)(i % ST_DEPTH));
+    }
+};
+
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256) bn_apply_stream_kernel(const bf16* __restrict__ y, float* __restrict__ mean_invstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const bf16* __restrict__ res, bf16* __restrict__ z, long long M, int C,
+                                                              int relu, const float* __restrict__ sums, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var, long long* __restrict__ nbt, float eps,
+                                                              float momentum, unsigned char* __restrict__ zmask, int interleaved) {
+    pdl_sync();
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ uint64_t st_full[ST_DEPTH];
+    constexpr int NT = HAS_RES ? 2 : 1;
+    const int cvec = C >> 3;
+    const int cv = threadIdx.x & (cvec - 1);
+    StreamRing<NT> ring;
+    ring.smem = st_smem;
+    ring.full = st_full;
+    ring.src[0] = reinterpret_cast<const uint8_t*>(y);
+    if (HAS_RES) ring.src[NT - 1] = reinterpret_cast<const uint8_t*>(res);
+    ring.plan(M * cvec, interleaved);
+    ring.start();
+
+    float sc[8], sh[8];
+    if (sums) {
+        const float inv_m = 1.f / (float)M;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            const float mean = sums[c] * inv_m;
+            const float var = fmaxf(sums[C + c] * inv_m - mean * mean, 0.f);
+            const float invstd = rsqrtf(var + eps);
+            if (blockIdx.x == 0 && threadIdx.x < cvec) {
+                mean_invstd[c] = mean;
+                mean_invstd[C + c] = invstd;
+                if (running_mean) {
+                    const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+                }
+            }
+            sc[i] = gamma[c] * invstd;
+            sh[i] = beta[c] - mean * sc[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            sc[i] = gamma[c] * mean_invstd[C + c];
+            sh[i] = beta[c] - mean_invstd[c] * sc[i];
+        }
+    }
+    for (long long i = 0; i < ring.c_count; ++i) {
+        const long long v = ring.chunk(i) * 256 + threadIdx.x;
+        ring.wait(i);
+        float f[8];
+        if (v < ring.nvec) {
+            unpack8(lds8(ring.slot_ptr(i, 0)), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = f[k] * sc[k] + sh[k];
+            if (HAS_RES) {
+                float rr[8];
+                unpack8(lds8(ring.slot_ptr(i, NT - 1)), rr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] += rr[k];
+            }
+        }
+        ring.release(i);
+        if (v < ring.nvec) {
+            if (relu) {
+                if (zmask) {
+                    unsigned int bits = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bits |= (f[k] > 0.f ? 1u : 0u) << k;
+                    zmask[v] = (unsigned char)bits;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+            }
+            st8(z + v * 8, pack8(f));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row, D <= 1024, D % 8 == 0: row kept in registers (<= 4 vectors of 8 per lane).
 constexpr int LN_MAXV = 4;
@@ -552,6 +707,18 @@ __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __res
 }
 
 bool bn_shape_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= 256 && 256 % (C / 8) == 0; }
+// DFU_BN_STREAM=0: register-staged kernels only
+const bool g_bn_stream = []() { const char* e = getenv("DFU_BN_STREAM"); return !(e && e[0] == '0'); }();
+// blocks of a streaming kernel: `per_sm` resident blocks, each with a contiguous range of 4 KB chunks
+inline int stream_grid(long long nvec, int per_sm) { return grid_cap((nvec + 255) / 256, per_sm); }
+const int g_stream_interleaved = []() { const char* e = getenv("DFU_STREAM_INTERLEAVED"); return e ? atoi(e) : 1; }();
+const int g_stream_per_sm = []() { const char* e = getenv("DFU_STREAM_PER_SM"); return e ? atoi(e) : 0; }();
+// resident blocks per SM (measured, profiles/r02j_bn_stream_sweep.txt): 2 for the >= 64 MB tensors of layer1 / layer2, 4 below
+inline int stream_per_sm(long long nvec) { return g_stream_per_sm > 0 ? g_stream_per_sm : (nvec >= (4ll << 20) ? 2 : 4); }
+template <typename K>
+inline void stream_smem_attr(K kernel, size_t bytes) {
+    if (bytes > 40 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   // + static barriers
+}
 
 
 // Eval-mode BatchNorm folded into the preceding convolution's weights: one block per output channel.
@@ -599,6 +766,20 @@ extern "C" int dfu_bn_apply(const void* y, const float* mean_invstd, const float
     DFU_CHECK_ARG(y && mean_invstd && gamma && beta && z && M > 0 && bn_shape_ok(C), "dfu_bn_apply: unsupported shape M=%lld C=%d",
                   (long long)M, C);
     const int rpi = 256 / (C / 8);
+    if (g_bn_stream) {
+        const long long nvec = M * (C / 8);
+        const int grid = stream_grid(nvec, stream_per_sm(nvec));
+        if (res) {
+            const size_t smem = (size_t)ST_DEPTH * 2 * ST_CHUNK;
+            stream_smem_attr(bn_apply_stream_kernel<true>, smem);
+            dfu_launch(bn_apply_stream_kernel<true>, grid, 256, smem, (cudaStream_t)stream, (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu,
+                       (const float*)nullptr, (float*)nullptr, (float*)nullptr, (long long*)nullptr, 0.f, 0.f, zmask, g_stream_interleaved);
+        } else {
+            const size_t smem = (size_t)ST_DEPTH * ST_CHUNK;
+            dfu_launch(bn_apply_stream_kernel<false>, grid, 256, smem, (cudaStream_t)stream, (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu,
+                       (const float*)nullptr, (float*)nullptr, (float*)nullptr, (long long*)nullptr, 0.f, 0.f, zmask, g_stream_interleaved);
+        }
+    } else
     dfu_launch(bn_apply_kernel, grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, const_cast<float*>(mean_invstd), gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, nullptr, nullptr,
         nullptr, nullptr, 0.f, 0.f, zmask);
     DFU_CHECK_LAUNCH("bn_apply");
@@ -611,6 +792,20 @@ extern "C" int dfu_bn_apply_train(const void* y, const float* sums, const float*
                   "dfu_bn_apply_train: unsupported shape M=%lld C=%d", (long long)M, C);
     DFU_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "dfu_bn_apply_train: running_mean/var go together");
     const int rpi = 256 / (C / 8);
+    if (g_bn_stream) {
+        const long long nvec = M * (C / 8);
+        const int grid = stream_grid(nvec, stream_per_sm(nvec));
+        if (res) {
+            const size_t smem = (size_t)ST_DEPTH * 2 * ST_CHUNK;
+            stream_smem_attr(bn_apply_stream_kernel<true>, smem);
+            dfu_launch(bn_apply_stream_kernel<true>, grid, 256, smem, (cudaStream_t)stream, (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu,
+                       sums, running_mean, running_var, (long long*)num_batches_tracked, eps, momentum, zmask, g_stream_interleaved);
+        } else {
+            const size_t smem = (size_t)ST_DEPTH * ST_CHUNK;
+            dfu_launch(bn_apply_stream_kernel<false>, grid, 256, smem, (cudaStream_t)stream, (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu,
+                       sums, running_mean, running_var, (long long*)num_batches_tracked, eps, momentum, zmask, g_stream_interleaved);
+        }
+    } else
     dfu_launch(bn_apply_kernel, grid_cap((M + rpi - 1) / rpi, 8), 256, 0, (cudaStream_t)stream, (const bf16*)y, mean_invstd, gamma, beta, (const bf16*)res, (bf16*)z, M, C, relu, sums, running_mean, running_var,
         (long long*)num_batches_tracked, eps, momentum, zmask);
     DFU_CHECK_LAUNCH("bn_apply_train");
