@@ -836,8 +836,8 @@ extern "C" int dfu_bn_bwd_apply(const void* dz, const void* z, const uint8_t* zm
 extern "C" int dfu_layernorm(const void* x, const float* gamma, const float* beta, void* y, float* stats, int64_t rows,
                              int32_t D, float eps, void* stream) {
     DFU_CHECK_ARG(x && gamma && beta && y && rows > 0 && D % 8 == 0 && D <= LN_MAXV * 256, "dfu_layernorm: unsupported D=%d", D);
-    const int grid = grid_cap((rows + 7) / 8, 3);
     const int nv = (D / 8 + 31) / 32;
+    const int grid = grid_cap((rows + 7) / 8, 3);
 #define DFU_LN_FWD(NV) dfu_launch(layernorm_kernel<NV>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, gamma, beta, (bf16*)y, stats, rows, D, eps)
     if (nv == 1) DFU_LN_FWD(1);
     else if (nv == 2) DFU_LN_FWD(2);

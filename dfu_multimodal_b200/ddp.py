@@ -19,7 +19,11 @@ def _default_cast(src_f32, dst_bf16):
 
 class GradBucketer:
     def __init__(self, params, process_group=None, bucket_bytes=BUCKET_BYTES, cast_fn=None, average=True,
-                 comm_stream=None):
+                 comm_stream=None, overlap=True):
+        """overlap=True: a bucket's all-reduce starts as soon as its last gradient is there, beside the rest of backward.
+        overlap=False: the all-reduces start together when backward is done (flush / finish_step) and only overlap the
+        bucket-by-bucket optimizer update -- no NCCL CTAs compete with the persistent GEMMs of backward for SMs."""
+        self.overlap = overlap
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.cast_fn = cast_fn or _default_cast
@@ -55,6 +59,7 @@ class GradBucketer:
         self.got = set()          # parameters that produced a gradient since begin_step()
         self.works = []
         self.events = [None] * len(self.buckets)     # bucket -> CUDA event recorded behind its all-reduce
+        self.launched = [False] * len(self.buckets)
         self.is_cuda = params[0].is_cuda
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream() if self.is_cuda else None)
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
@@ -66,6 +71,7 @@ class GradBucketer:
         self.got = set()
         self.works = []
         self.events = [None] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
 
     def _on_grad(self, p):
         bi, off, n = self.slot[p]
@@ -78,10 +84,11 @@ class GradBucketer:
             # the two model branches may run backward on different streams; remember every producer stream
             self.producers[bi].add(torch.cuda.current_stream())
         self.pending[bi] -= 1
-        if self.pending[bi] == 0:
+        if self.pending[bi] == 0 and self.overlap:
             self._launch(bi)
 
     def _launch(self, bi):
+        self.launched[bi] = True
         if self.world == 1:
             return
         flat = self.flat[bi]
@@ -125,6 +132,8 @@ class GradBucketer:
 
     def _flush_pending(self):
         for bi, left in enumerate(self.pending):
+            if self.launched[bi]:
+                continue
             if left > 0:
                 # some parameters of this bucket received no gradient this step (frozen or conditionally used): their
                 # slices still hold LAST step's reduced gradient -- clear them so the all-reduce moves zeros, and
@@ -134,7 +143,7 @@ class GradBucketer:
                         _, off, n = self.slot[p]
                         self.flat[bi][off:off + n].zero_()
                 self.pending[bi] = 0
-                self._launch(bi)
+            self._launch(bi)                         # (deferred mode: complete buckets go out here too, in bucket order)
 
     def grad_source(self, p):
         """For FusedAdamW.set_grad_source: (bf16 grad slice, is_bf16, scale)."""

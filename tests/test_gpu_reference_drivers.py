@@ -3,13 +3,10 @@ extended_metrics.py drivers").  `notebooks/train_multimodal_fusion.py` (script b
 `notebooks/extended_metrics.py` (main :649-867) are executed unmodified with runpy against a synthetic data tree
 (tools/synthetic_tree.py) with HOME redirected; the only substitutions are the two constructors the scripts call
 (dropin.install(): torch.hub.load -> DfuResNet50, timm.create_model -> DfuVisionTransformer) and a matplotlib stub (the
-image has no matplotlib).  The scripts come from /root/reference when it exists, else from the byte-identical staged copy
-in the git-ignored oracle/_ref/ (oracle/stage_reference.py; sha256 checked here); without either the tests skip."""
-import hashlib
-import json
+image has no matplotlib).  The scripts come from /root/reference when it exists, else from the archive staged in the
+git-ignored oracle/_ref/ (oracle/stage_reference.py; sha256 of every member checked); without either the tests skip."""
 import os
 import runpy
-import shutil
 import sys
 
 import pytest
@@ -20,35 +17,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _reference_base():
+def _materialize_drivers(dest):
     sys.path.insert(0, ROOT)
     from oracle import stage_reference
-    base = stage_reference.locate()
+    base = stage_reference.materialize(dest)          # from /root/reference, else from the staged archive (sha256 checked)
     if base is None:
-        pytest.skip("reference drivers not available (no /root/reference and no staged oracle/_ref/notebooks)")
-    man = os.path.join(base, "MANIFEST.json")
-    if os.path.exists(man):                                   # staged copy: must be byte-identical to what was staged
-        with open(man) as f:
-            want = json.load(f)["sha256"]
-        for rel, sha in want.items():
-            with open(os.path.join(base, rel), "rb") as f:
-                assert hashlib.sha256(f.read()).hexdigest() == sha, "staged reference driver was modified: " + rel
+        pytest.skip("reference drivers not available (no /root/reference and no oracle/_ref/reference_drivers.tar.gz)")
     return base
 
 
 @pytest.fixture(scope="module")
 def driver_run(tmp_path_factory):
     """Runs the training script once (10 epochs on a tiny tree, as its constants say) and hands its namespace on."""
-    base = _reference_base()
     from dfu_multimodal_b200 import dropin
     from _stubs import install_matplotlib_stub
     from tools.synthetic_tree import make_tree
     home = str(tmp_path_factory.mktemp("home"))
     make_tree(home, seed=3)
     proj = os.path.join(home, "CompVis", "DFU_MMT")          # extended_metrics.py reads <its parent dir>/logs
-    os.makedirs(os.path.join(proj, "notebooks"))
-    for name in ("train_multimodal_fusion.py", "extended_metrics.py"):
-        shutil.copyfile(os.path.join(base, "notebooks", name), os.path.join(proj, "notebooks", name))
+    _materialize_drivers(proj)                               # proj/notebooks/{train_multimodal_fusion,extended_metrics}.py
     old_home, old_argv = os.environ.get("HOME"), sys.argv
     os.environ["HOME"] = home
     stubs = install_matplotlib_stub()
