@@ -598,6 +598,7 @@ def main():
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU comparator")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--ddp-defer", action="store_true", help="N > 1: start the gradient all-reduces after backward instead of beside it")
+    ap.add_argument("--bucket-mb", type=int, default=0, help="N > 1: gradient bucket size in MB (0 = ddp.BUCKET_BYTES)")
     ap.add_argument("--vit-sms", type=int, default=0, help="SM budget of the ViT branch stream (0 = whole device)")
     ap.add_argument("--resnet-sms", type=int, default=0, help="SM budget of the ResNet branch stream")
     ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks to stderr after this many seconds")
@@ -650,7 +651,8 @@ def main():
     opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
     bucketer = None
     if world > 1:
-        bucketer = GradBucketer(list(model.parameters()), overlap=not args.ddp_defer)
+        bucketer = GradBucketer(list(model.parameters()), overlap=not args.ddp_defer,
+                                **({"bucket_bytes": args.bucket_mb << 20} if args.bucket_mb else {}))
         opt.set_grad_source(bucketer.grad_source, bucketer)
     # synthetic data: 2 distinct batches alternate so no step re-reads the previous step's inputs from L2
     host = []
