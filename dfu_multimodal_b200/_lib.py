@@ -63,6 +63,10 @@ class AdamWTensor(ctypes.Structure):
                 ("shadow", ctypes.c_void_p), ("numel", ctypes.c_int64)]
 
 
+class CastTensor(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("numel", ctypes.c_int64)]
+
+
 _SCALARS = {
     "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float, "double": ctypes.c_double,
     "int": ctypes.c_int,

@@ -136,6 +136,30 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
     }
 }
 
+// Multi-tensor fp32 -> bf16 cast: one block per chunk of `chunk_size` elements of one tensor (the gradients of a whole
+// data-parallel bucket go onto the wire with ONE launch instead of one per parameter).
+__global__ void __launch_bounds__(256) cast_multi_kernel(const dfu_cast_tensor* __restrict__ table, const int* __restrict__ chunk_tensor,
+                                                         const int* __restrict__ chunk_offset, int chunk_size) {
+    pdl_sync();
+    const dfu_cast_tensor t = table[chunk_tensor[blockIdx.x]];
+    const long long start = (long long)chunk_offset[blockIdx.x] * chunk_size;
+    const long long end = min(start + chunk_size, (long long)t.numel);
+    const float* src = t.src;
+    bf16* dst = reinterpret_cast<bf16*>(t.dst);
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const long long v0 = start >> 3, v1 = end >> 3;     // chunk_size is a multiple of 8
+        for (long long i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i * 2);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src) + i * 2 + 1);
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            st8(dst + i * 8, pack8(f));
+        }
+        for (long long i = (v1 << 3) + threadIdx.x; i < end; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
+    } else {
+        for (long long i = start + threadIdx.x; i < end; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
+    }
+}
+
 // Multi-tensor: one block per chunk of `chunk_size` elements of one tensor.
 template <bool G_BF16>
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const dfu_adamw_tensor* __restrict__ table,
@@ -308,6 +332,14 @@ extern "C" int dfu_adamw(const dfu_adamw_tensor* table, int32_t n_tensors, const
         dfu_launch(adamw_multi_kernel<false>, n_chunks, 256, 0, (cudaStream_t)stream, table, chunk_tensor, chunk_offset, chunk_size, step, lr,
                                                                              beta1, beta2, eps, weight_decay, grad_scale);
     DFU_CHECK_LAUNCH("dfu_adamw");
+    return DFU_OK;
+}
+extern "C" int dfu_cast_multi_f32_bf16(const dfu_cast_tensor* table, int32_t n_tensors, const int32_t* chunk_tensor,
+                                       const int32_t* chunk_offset, int32_t n_chunks, int32_t chunk_size, void* stream) {
+    DFU_CHECK_ARG(table && n_tensors > 0 && chunk_tensor && chunk_offset && n_chunks > 0 && chunk_size > 0 && chunk_size % 8 == 0,
+                  "dfu_cast_multi_f32_bf16: bad args");
+    dfu_launch(cast_multi_kernel, n_chunks, 256, 0, (cudaStream_t)stream, table, chunk_tensor, chunk_offset, chunk_size);
+    DFU_CHECK_LAUNCH("dfu_cast_multi_f32_bf16");
     return DFU_OK;
 }
 extern "C" int dfu_adamw_flat(float* p, const void* g, float* m, float* v, void* shadow, int64_t n, const float* step, float lr,

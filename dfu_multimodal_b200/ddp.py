@@ -12,9 +12,49 @@ from . import ops
 BUCKET_BYTES = 25 * 1024 * 1024
 
 
+CAST_CHUNK = 65536
+
+
 def _default_cast(src_f32, dst_bf16):
     """fp32 gradient (dense, any dim order) -> bf16 bucket slice in storage order, with our cast kernel."""
     ops.cast_f32_bf16(src_f32, 1, src_f32.numel(), src_f32.numel(), out=dst_bf16)
+
+
+class _BucketCaster:
+    """All gradients of a bucket -> its bf16 wire buffer with ONE dfu_cast_multi_f32_bf16 launch (317 per-parameter cast
+    launches per step otherwise).  The device pointer tables are cached per (bucket, gradient addresses): inside a captured
+    CUDA graph the addresses are fixed, so each table is built once."""
+
+    def __init__(self):
+        self.tables = {}
+
+    def __call__(self, bi, grads, dsts):
+        import ctypes
+        from . import _lib
+        from ._lib import CastTensor, check
+        key = (bi, tuple(g.data_ptr() for g in grads))
+        ent = self.tables.get(key)
+        if ent is None:
+            n = len(grads)
+            arr = (CastTensor * n)()
+            ct, co = [], []
+            for i, (g, d) in enumerate(zip(grads, dsts)):
+                arr[i].src, arr[i].dst, arr[i].numel = g.data_ptr(), d.data_ptr(), g.numel()
+                for c in range((g.numel() + CAST_CHUNK - 1) // CAST_CHUNK):
+                    ct.append(i)
+                    co.append(c)
+            host = [torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory(),
+                    torch.tensor(ct, dtype=torch.int32).pin_memory(), torch.tensor(co, dtype=torch.int32).pin_memory()]
+            dev = [h.to(grads[0].device, non_blocking=True) for h in host]       # memcpy nodes under graph capture
+            ent = dict(host=host, dev=dev, n=n, n_chunks=len(ct), captured=torch.cuda.is_current_stream_capturing())
+            eager = [k for k, e in self.tables.items() if not e["captured"]]
+            for k in eager[:max(0, len(eager) - 64)]:
+                del self.tables[k]
+            self.tables[key] = ent
+        t, c, o = ent["dev"]
+        check(_lib.load().dfu_cast_multi_f32_bf16(t.data_ptr(), ent["n"], c.data_ptr(), o.data_ptr(), ent["n_chunks"], CAST_CHUNK,
+                                                  torch.cuda.current_stream().cuda_stream), "cast_multi_f32_bf16")
+        ops._count()
 
 
 class GradBucketer:
@@ -27,6 +67,8 @@ class GradBucketer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.cast_fn = cast_fn or _default_cast
+        # CUDA + our own cast: the gradients of a bucket are cast together when the bucket is complete
+        self.bucket_caster = _BucketCaster() if cast_fn is None else None
         self.average = average
         params = [p for p in params if p.requires_grad]
         self.params = params
@@ -60,6 +102,7 @@ class GradBucketer:
         self.works = []
         self.events = [None] * len(self.buckets)     # bucket -> CUDA event recorded behind its all-reduce
         self.launched = [False] * len(self.buckets)
+        self.ready = [[] for _ in self.buckets]      # (gradient, wire slice) pairs waiting for the bucket's one cast launch
         self.is_cuda = params[0].is_cuda
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream() if self.is_cuda else None)
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
@@ -72,20 +115,40 @@ class GradBucketer:
         self.works = []
         self.events = [None] * len(self.buckets)
         self.launched = [False] * len(self.buckets)
+        self.ready = [[] for _ in self.buckets]
 
     def _on_grad(self, p):
         bi, off, n = self.slot[p]
         self.got.add(p)
         g = p.grad
-        if g.stride() != p.stride():
+        same_order = all(gs == ps for gs, ps, k in zip(g.stride(), p.stride(), p.shape) if k > 1)   # size-1 dims carry any stride
+        if not same_order:
             g = g.contiguous() if p.is_contiguous() else torch.empty_like(p).copy_(g)
-        self.cast_fn(g, self.flat[bi][off:off + n])
+        batched = self.bucket_caster is not None and self.is_cuda and g.dtype == torch.float32
+        if batched:
+            self.ready[bi].append((g, self.flat[bi][off:off + n]))
+        else:
+            self.cast_fn(g, self.flat[bi][off:off + n])
         if self.is_cuda:
             # the two model branches may run backward on different streams; remember every producer stream
             self.producers[bi].add(torch.cuda.current_stream())
         self.pending[bi] -= 1
-        if self.pending[bi] == 0 and self.overlap:
-            self._launch(bi)
+        if self.pending[bi] == 0:
+            self._cast_bucket(bi)
+            if self.overlap:
+                self._launch(bi)
+
+    def _cast_bucket(self, bi):
+        """One launch puts every gradient of the bucket on the wire buffer (on the current stream, after the other producers)."""
+        if not self.ready[bi]:
+            return
+        cur = torch.cuda.current_stream()
+        for s in self.producers[bi]:
+            if s != cur:
+                cur.wait_stream(s)
+        grads, dsts = zip(*self.ready[bi])
+        self.bucket_caster(bi, grads, dsts)
+        self.ready[bi] = []
 
     def _launch(self, bi):
         self.launched[bi] = True
@@ -143,6 +206,8 @@ class GradBucketer:
                         _, off, n = self.slot[p]
                         self.flat[bi][off:off + n].zero_()
                 self.pending[bi] = 0
+                if self.is_cuda:
+                    self._cast_bucket(bi)
             self._launch(bi)                         # (deferred mode: complete buckets go out here too, in bucket order)
 
     def grad_source(self, p):

@@ -241,6 +241,13 @@ int dfu_adamw(const dfu_adamw_tensor* table, int32_t n_tensors, const int32_t* c
               const int32_t* chunk_offset, int32_t n_chunks, int32_t chunk_size, const float* step, float lr,
               float beta1, float beta2, float eps, float weight_decay, float grad_scale, int32_t g_bf16,
               void* stream);
+/* Multi-tensor fp32 -> bf16 cast in storage order (same chunk tables as dfu_adamw): the fp32 gradients of one data-parallel
+ * bucket are written into the bucket's bf16 wire buffer with one launch (replaces one aten::_to_copy per parameter). */
+typedef struct {
+    const float* src; void* dst; int64_t numel;
+} dfu_cast_tensor;
+int dfu_cast_multi_f32_bf16(const dfu_cast_tensor* table, int32_t n_tensors, const int32_t* chunk_tensor,
+                            const int32_t* chunk_offset, int32_t n_chunks, int32_t chunk_size, void* stream);
 /* Flat variant over one contiguous fp32 parameter arena. */
 int dfu_adamw_flat(float* p, const void* g, float* m, float* v, void* shadow, int64_t n, const float* step,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,

@@ -149,5 +149,6 @@ def test_n_gpu_step_equals_one_gpu_micro_batched_step(world, tmp_path):
     # SAME single-GPU step differ by as much)
     assert min(cosines.values()) > 0.9, cosines
     # BatchNorm statistics stay per rank: rank 0's are those of the 1-GPU model after micro-batch 0 alone
+    # (two executions: the deep layers' batch statistics differ in the third digit, see the gradient cosines above)
     for n, b in buffers0.items():
-        assert torch.allclose(got[0]["buffers"][n].float(), b.float(), rtol=2e-3, atol=2e-4), n
+        assert torch.allclose(got[0]["buffers"][n].float(), b.float(), rtol=2e-2, atol=2e-3), n
