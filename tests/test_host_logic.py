@@ -209,3 +209,108 @@ def test_abi_rejects_unsupported_convolution_and_epilogue_combinations_without_a
     g.act = 4                                            # GELU with derivative output needs aux
     assert L.dfu_gemm(ctypes.byref(g), None) != 0
     assert b"act=4" in L.dfu_last_error()
+
+
+# ----------------------------------------------------------------------------------------------- round 2: host logic of f1 / f2 / f4
+def test_paired_dataset_and_sampler_follow_the_reference(tmp_path):
+    """data.PairedFolderDataset == MultimodalDataset's pairing (train_multimodal_fusion.py:108-140) on a synthetic tree."""
+    import os
+    import random
+    from dfu_multimodal_b200.data import PairedFolderDataset, class_weights, weighted_sample_indices
+    from tools.synthetic_tree import make_tree
+    data, files = make_tree(str(tmp_path), counts={"train": 3, "val": 2, "test": 2}, seed=1)
+    assert len(files) == 2 * 2 * (3 + 2 + 2) + 2 * 3            # thermal holds one image more per class and split
+    ds = PairedFolderDataset(os.path.join(data, "rgb"), os.path.join(data, "thermal"), "train", random.Random(42))
+    assert len(ds) == 8 and ds.labels.count(0) == 4 and ds.labels.count(1) == 4
+    healthy = [(os.path.basename(r), os.path.basename(t)) for r, t, y in ds.pairs if y == 0]
+    # 3 RGB against 4 thermal images: pair i = (rgb[i % 3], thermal[i % 4])
+    assert sorted(healthy) == sorted([("rgb_train_healthy_%03d.png" % (i % 3), "thermal_train_healthy_%03d.png" % i) for i in range(4)])
+    rgb, th, y = ds.load(0)
+    assert rgb.dtype.name == "uint8" and rgb.ndim == 3 and rgb.shape[2] == 3 and th.shape[2] == 3 and y in (0, 1)
+    assert torch.allclose(class_weights([0, 0, 0, 1]), torch.tensor([4 / 3, 4.0]))
+    idx = weighted_sample_indices([0] * 30 + [1] * 2, torch.Generator().manual_seed(3))
+    assert len(idx) == 32 and 8 <= sum(1 for i in idx if i >= 30) <= 24         # classes are drawn about equally often
+
+
+def test_augmentation_parameter_packing_matches_the_pillow_maps():
+    """augment.pack_params builds the same 16.16 fixed-point inverse maps as the oracle's restatement of Pillow / torchvision."""
+    import ctypes
+    import random
+    from dfu_multimodal_b200 import augment as G
+    from dfu_multimodal_b200._lib import AugmentParams
+    from oracle import augment_pil as A
+    rng = random.Random(3)
+    ps = G.draw_params(100, "rgb", rng=rng)
+    ps += [{"hflip": False, "vflip": True, "angle": 0.0, "affine": {"angle": 0.0, "translate": (3, -4), "scale": 1.1}},
+           {"hflip": True, "vflip": False, "angle": 180.0}, {"hflip": True, "vflip": False, "angle": 90.0}]
+    packed = G.pack_params(ps)
+    arr = (AugmentParams * len(ps)).from_buffer_copy(packed.numpy().tobytes())
+    assert packed.numel() == len(ps) * ctypes.sizeof(AugmentParams)
+    for rec, p in zip(arr, ps):
+        assert rec.flags == (1 if p["hflip"] else 0) | (2 if p["vflip"] else 0)
+        if p["angle"] % 360.0 not in (0, 90, 180, 270):
+            assert rec.rot_kind == 1 and list(rec.rot) == A.fixed_coeffs(A.rotate_matrix(p["angle"], 224, 224))
+        if "affine" in p and rec.aff_kind == 1:
+            a = p["affine"]
+            assert list(rec.aff) == A.fixed_coeffs(A.inverse_affine_matrix(a["angle"], a["translate"], a["scale"], 224, 224))
+        if "jitter" in p:
+            assert rec.n_color == 3 and list(rec.color_op) == p["jitter"]["order"]
+    assert [r.rot_kind for r in arr[-3:]] == [0, 2, 3] and arr[-3].aff_kind == 5
+    assert list(arr[-3].aff_xtab[:3]) == [int(3 * 0 + (112 - 112 / 1.1 - 3 / 1.1 + 0.5 / 1.1 + k / 1.1)) for k in range(3)]
+    assert not any("jitter" in p for p in G.draw_params(50, "thermal", rng=rng))
+
+
+def test_fused_adamw_state_dict_is_a_torch_adamw_state_dict():
+    """The schema half of resume (f4) needs no GPU: FusedAdamW.state_dict() loads into torch.optim.AdamW and steps like it."""
+    from dfu_multimodal_b200.optim import FusedAdamW
+
+    def make():
+        g = torch.Generator().manual_seed(7)
+        return [nn.Parameter(torch.randn(s, generator=g)) for s in [(6, 4, 3, 3), (5,)]]
+
+    def run(opt, ps, steps):
+        for st in steps:
+            g = torch.Generator().manual_seed(100 + st)
+            for p in ps:
+                p.grad = torch.randn(p.shape, generator=g)
+            opt.step()
+    a = make()
+    oa = torch.optim.AdamW(a, lr=1e-3, weight_decay=1e-2)
+    run(oa, a, range(5))
+    c = [nn.Parameter(p.detach().clone()) for p in a]
+    oc = FusedAdamW(c, lr=1e-3, weight_decay=1e-2)
+    step = torch.tensor(5.0)
+    oc._steps[("cpu", None)] = step
+    for p, q in zip(c, a):
+        oc.state[p] = {"step": step, "exp_avg": oa.state[q]["exp_avg"].clone(), "exp_avg_sq": oa.state[q]["exp_avg_sq"].clone()}
+    sd = oc.state_dict()
+    assert sd["param_groups"][0]["decoupled_weight_decay"] is True and float(sd["state"][0]["step"]) == 5.0
+    assert sd["state"][0]["step"] is not sd["state"][1]["step"]                   # per-parameter copies, like torch's
+    d = [nn.Parameter(p.detach().clone()) for p in c]
+    od = torch.optim.AdamW(d, lr=1e-3, weight_decay=1e-2)
+    od.load_state_dict(sd)
+    run(od, d, [5])
+    run(oa, a, [5])
+    assert all(torch.equal(p, q) for p, q in zip(a, d))
+    with pytest.raises(RuntimeError):
+        oc.step()                                                                 # ... and the update itself has no CPU path
+
+
+def test_staged_reference_archive_unpacks_to_the_recorded_hashes(tmp_path):
+    import hashlib
+    import os
+    from oracle import stage_reference as S
+    if not os.path.exists(S.ARCHIVE):
+        pytest.skip("no staged archive (oracle/_ref is built by __graft_entry__.build() where /root/reference exists)")
+    real = S.REFERENCE
+    S.REFERENCE = str(tmp_path / "absent")                                        # force the archive path
+    try:
+        dest = S.materialize(str(tmp_path / "out"))
+    finally:
+        S.REFERENCE = real
+    import json
+    with open(S.MANIFEST) as f:
+        want = json.load(f)["sha256"]
+    for rel, sha in want.items():
+        with open(os.path.join(dest, rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == sha
