@@ -42,6 +42,26 @@ __device__ __forceinline__ bf16x8 ld_global_v4(const void* p) {
     return *reinterpret_cast<bf16x8*>(&u);
 }
 
+// Phase tracing for tools/gpu_attn_trace.py (a separate library built with -DDFU_ATTN_TRACE; compiled out otherwise):
+// CTA 0 records clock64() at the phase boundaries of its MMA thread and of one thread per softmax group.
+#ifdef DFU_ATTN_TRACE
+__device__ long long g_attn_trace[4][16][12];
+#define ATTN_TR(role, it, ph)                                                                   \
+    do {                                                                                        \
+        if (blockIdx.x == 0 && (it) < 16 && (threadIdx.x & 31) == 0) g_attn_trace[role][it][ph] = clock64(); \
+    } while (0)
+// accumulating variant for the backward kernel: time since the previous mark goes to category `cat` of role 1
+#define ATTN_ACC(cat)                                                                           \
+    do {                                                                                        \
+        const long long now_ = clock64();                                                       \
+        if (trb) g_attn_trace[3][it < 15 ? it : 15][cat] += now_ - tprev;                        \
+        tprev = now_;                                                                           \
+    } while (0)
+#else
+#define ATTN_TR(role, it, ph) ((void)0)
+#define ATTN_ACC(cat) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int F_Q0 = 0, F_Q1 = TILE128_BYTES, F_K = 2 * TILE128_BYTES, F_V = F_K + KV_BYTES, F_P0 = F_V + KV_BYTES,
               F_P1 = F_P0 + 4 * TILE128_BYTES, F_END = F_P1 + 4 * TILE128_BYTES;
@@ -49,7 +69,7 @@ constexpr int FWD_SMEM = F_END + 1024;
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int H, float scale) {
+                const __grid_constant__ CUtensorMap map_o, float* __restrict__ lse, int B, int T, int H, float scale) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t qk_full, qk_empty, v_full, v_empty, s_full[2], p_full[2], o_full[2], o_empty[2];
@@ -60,7 +80,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int NK = (T + 15) & ~15;            // key columns of S (multiple of 16)
     const int items = B * H;
 
-    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_q); prefetch_tmap(&map_kv); }
+    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_q); prefetch_tmap(&map_kv); prefetch_tmap(&map_o); }
     if (warp_idx == 1 && lane == 0) {
         mbar_init(&qk_full, 1); mbar_init(&qk_empty, 1); mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -99,40 +119,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc(128, NK, 0, 0);
-            const uint32_t idesc_o = make_idesc(128, HD, 0, 1);
-            const uint32_t sQ = smem_u32(smem + F_Q0), sK = smem_u32(smem + F_K), sV = smem_u32(smem + F_V),
-                           sP = smem_u32(smem + F_P0);
-            const int nks = NK / 16;
-            int it = 0;
-            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
-                mbar_wait(&qk_full, ph);
-                tc_fence_after();
-                for (int i = 0; i < 2; ++i) {
-                    mbar_wait(&o_empty[i], ph ^ 1);      // the previous head's O_i has been read out of TMEM
-                    tc_fence_after();
+        // The whole warp walks the loop and waits; one elected lane issues the MMAs and their commits.
+        const uint32_t idesc_s = make_idesc(128, NK, 0, 0);
+        const uint32_t idesc_o = make_idesc(128, HD, 0, 1);
+        const uint32_t sQ = smem_u32(smem + F_Q0), sK = smem_u32(smem + F_K), sV = smem_u32(smem + F_V),
+                       sP = smem_u32(smem + F_P0);
+        const int nks = NK / 16;
+        const uint64_t dQ0 = make_desc(sQ, 16, 1024), dK0 = make_desc(sK, 16, 1024);
+        const uint64_t dP0 = make_desc(sP, 16, 1024), dV0 = make_desc(sV, 8192, 1024);
+        auto issue_s = [&](int i) {
+            if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        tc_mma_f16(tmem + i * 256, make_desc(sQ + i * TILE128_BYTES + k * 32, 16, 1024),
-                                   make_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
-                    tc_commit(&s_full[i]);
-                }
-                tc_commit(&qk_empty);                    // Q and K may be overwritten once both S tiles are done
-                mbar_wait(&v_full, ph);
-                tc_fence_after();
-                for (int i = 0; i < 2; ++i) {
-                    mbar_wait(&p_full[i], ph);           // softmax warps wrote P_i (and finished reading S_i)
-                    tc_fence_after();
-                    for (int k = 0; k < nks; ++k)
-                        tc_mma_f16(tmem + i * 256,
-                                   make_desc(sP + i * 4 * TILE128_BYTES + (k >> 2) * TILE128_BYTES + (k & 3) * 32, 16, 1024),
-                                   make_desc(sV + k * 2048, 8192, 1024), idesc_o, k > 0);
-                    tc_commit(&o_full[i]);
-                }
-                tc_commit(&v_empty);
+                for (int k = 0; k < HD / 16; ++k)
+                    tc_mma_f16(tmem + i * 256, dQ0 + (uint64_t)((i * TILE128_BYTES + k * 32) >> 4), dK0 + (uint64_t)((k * 32) >> 4),
+                               idesc_s, k > 0);
+                tc_commit(&s_full[i]);
+                if (i == 1) tc_commit(&qk_empty);        // Q and K may be overwritten once both S tiles are done
             }
+            __syncwarp();
+        };
+        auto issue_o = [&](int i) {
+            if (elect_one()) {
+                // 13 MMAs of 32 tensor clocks each: descriptors = base + compile-time offset, nothing else per issue
+#pragma unroll
+                for (int k = 0; k < KV_ROWS / 16; ++k)
+                    if (k < nks)
+                        tc_mma_f16(tmem + i * 256,
+                                   dP0 + (uint64_t)((i * 4 * TILE128_BYTES + (k >> 2) * TILE128_BYTES + (k & 3) * 32) >> 4),
+                                   dV0 + (uint64_t)((k * 2048) >> 4), idesc_o, k > 0);
+                tc_commit(&o_full[i]);
+                if (i == 1) tc_commit(&v_empty);         // V may be overwritten once both O tiles are done
+            }
+            __syncwarp();
+        };
+        // The two query tiles run half a head apart: S0(h), O1(h-1), S1(h), O0(h), ...  While one softmax group is in its
+        // exp pass (SFU-bound) the other is waiting for an MMA, reading O out or reducing its row maxima, instead of both
+        // groups hitting the same phase together and leaving the SFU idle in between.
+        int it = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            mbar_wait(&qk_full, ph);
+            mbar_wait(&o_empty[0], ph ^ 1);              // the previous head's O_0 has been read out of TMEM
+            tc_fence_after();
+            ATTN_TR(0, it, 0);
+            issue_s(0);
+            ATTN_TR(0, it, 1);
+            if (it > 0) {
+                mbar_wait(&p_full[1], ph ^ 1);           // previous head: softmax warps wrote P_1 (and finished reading S_1)
+                tc_fence_after();
+                ATTN_TR(0, it, 2);
+                issue_o(1);
+            }
+            ATTN_TR(0, it, 3);
+            mbar_wait(&o_empty[1], ph ^ 1);
+            tc_fence_after();
+            ATTN_TR(0, it, 4);
+            issue_s(1);
+            ATTN_TR(0, it, 5);
+            mbar_wait(&v_full, ph);
+            mbar_wait(&p_full[0], ph);
+            tc_fence_after();
+            ATTN_TR(0, it, 6);
+            issue_o(0);
+            ATTN_TR(0, it, 7);
+        }
+        if (it > 0) {                                    // drain: O_1 of the last head
+            mbar_wait(&p_full[1], (it - 1) & 1);
+            tc_fence_after();
+            issue_o(1);
         }
     } else if (warp_idx >= 4) {
         // 8 warps per query tile: two per TMEM lane quarter, each taking every other 32-column chunk of the row.
@@ -147,15 +201,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + i * 256;
         const int nchunks = (NK + 31) / 32;
         const int my_chunks = (nchunks - half + 1) / 2;  // chunks half, half+2, ...
+        const bool storer = (ew & 7) == 0 && lane == 0;  // issues the group's TMA store of O
         int it = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
             const int b = w / H, h = w - b * H;
+            const bool tr = (ew & 7) == 0 && lane == 0;  // one tracing thread per group
+            if (tr) ATTN_TR(1 + i, it, 0);
             mbar_wait(&s_full[i], ph);
             tc_fence_after();
+            if (tr) ATTN_TR(1 + i, it, 1);
             uint32_t ra[32], rb[32];
-            // pass 1: row maximum of the raw scores (the next chunk's TMEM load is in flight while this one is reduced)
-            float m = -INFINITY;
+            // pass 1: row maximum of the raw scores (the next chunk's TMEM load is in flight while this one is reduced;
+            // four independent chains so that the reduction is not one 104-deep dependency)
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             tmem_ld32(taddr + half * 32, ra);
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -167,20 +226,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     if (cc + 1 < my_chunks) tmem_ld32(taddr + (c + 2) * 32, nxt);
                     if (c * 32 + 32 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(cur[j]));
+                        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < T) m = fmaxf(m, __uint_as_float(cur[j]));
+                            if (c * 32 + j < T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
                     }
                 }
             }
+            float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             pmax_s[i][half][row] = m;
+            if (tr) ATTN_TR(1 + i, it, 2);
+            if (storer) bulk_wait_read0();               // the previous head's O tile has left the P_i buffer (see below)
             named_bar_sync(1 + i, 256);
+            if (tr) ATTN_TR(1 + i, it, 3);
             m = fmaxf(m, pmax_s[i][half ^ 1][row]);
-            // pass 2: p = exp(scale (s - m)), partial row sum, bf16 P into the K-major SWIZZLE_128B operand tile
+            // pass 2: p = exp(scale (s - m)), partial row sum, bf16 P into the K-major SWIZZLE_128B operand tile.  Only the
+            // chunk that straddles T pays for the key mask; the others are FFMA + EX2 + FADD + half a pack per score.
             const float ms = m * sl2;
-            float sum = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
             tmem_ld32(taddr + half * 32, ra);
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -190,52 +254,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     uint32_t* nxt = (cc & 1) ? ra : rb;
                     tmem_ld_wait();
                     if (cc + 1 < my_chunks) tmem_ld32(taddr + (c + 2) * 32, nxt);
-                    const bool full = c * 32 + 32 <= T;
+                    if (c * 32 + 32 <= T) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col0 = c * 32 + g * 8;
-                        if (col0 < NK) {                 // warp-uniform
+                        for (int g = 0; g < 4; ++g) {
+                            const int col0 = c * 32 + g * 8;
                             float p[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float e = ex2_approx(__uint_as_float(cur[g * 8 + j]) * sl2 - ms);
-                                p[j] = (full || col0 + j < T) ? e : 0.f;
-                                sum += p[j];
+                                p[j] = ex2_approx(__uint_as_float(cur[g * 8 + j]) * sl2 - ms);
+                                s4[j & 3] += p[j];
                             }
                             const int atom = col0 >> 6, cj = (col0 & 63) >> 3;
                             st_shared_v4(sP + atom * TILE128_BYTES + ((cj ^ (row & 7)) << 4), pack8(p));
                         }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int col0 = c * 32 + g * 8;
+                            if (col0 < NK) {             // warp-uniform
+                                float p[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float e = ex2_approx(__uint_as_float(cur[g * 8 + j]) * sl2 - ms);
+                                    p[j] = col0 + j < T ? e : 0.f;
+                                    s4[j & 3] += p[j];
+                                }
+                                const int atom = col0 >> 6, cj = (col0 & 63) >> 3;
+                                st_shared_v4(sP + atom * TILE128_BYTES + ((cj ^ (row & 7)) << 4), pack8(p));
+                            }
+                        }
                     }
                 }
             }
+            float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             psum_s[i][half][row] = sum;
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[i]);
+            if (tr) ATTN_TR(1 + i, it, 4);
             named_bar_sync(1 + i, 256);
+            if (tr) ATTN_TR(1 + i, it, 5);
             sum += psum_s[i][half ^ 1][row];
             if (half == 0 && q < T) lse[((long long)b * H + h) * T + q] = m * scale + __logf(sum);
-            // O = P V / rowsum: this warp stores 32 of the 64 output columns
+            // O = P V / rowsum.  A thread owns one row, so direct global stores would touch 32 different 128-byte lines per
+            // instruction (2 048 L1 wavefronts per head -- measured 2.4 k clocks); instead the bf16 rows are staged in the
+            // first atom of P_i (free once o_full fires: the MMA has read P) and leave through one TMA store per tile, which
+            // also clips the rows >= T of the second tile.
             mbar_wait(&o_full[i], ph);
             tc_fence_after();
+            if (tr) ATTN_TR(1 + i, it, 6);
             const float inv = 1.f / sum;
-            bf16* orow = out + ((long long)b * T + q) * (H * HD) + h * HD + half * 32;
             tmem_ld32(taddr + half * 32, ra);
             tmem_ld_wait();
-            if (q < T) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ra[g * 8 + j]) * inv;
-                    st_global_v4(orow + g * 8, pack8(v));
-                }
-            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[i]);
+            if (lane == 0) mbar_arrive(&o_empty[i]);     // TMEM columns of tile i are free for the next head's S
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ra[g * 8 + j]) * inv;
+                st_shared_v4(sP + (((half * 4 + g) ^ (row & 7)) << 4), pack8(v));
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + i, 256);
+            if (storer) {
+                tma_store_3d(&map_o, smem + (i ? F_P1 : F_P0), h * HD, i * 128, b);
+                bulk_commit();
+            }
+            if (tr) ATTN_TR(1 + i, it, 7);
         }
+        if (storer) bulk_wait0();                        // the last O tile is in global memory before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -495,29 +585,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 // per chunk and dQ per chunk PAIR (M = 128 queries, the two dS^T buffers read as one MN-major operand).
 constexpr int P_PT0 = 4 * KV_BYTES, P_DST0 = P_PT0 + 2 * TILE128_BYTES;      // PT[2] then DST[2], 16 KB each
 constexpr int P_SD = 0;                                                      // TMEM: buffer b -> S^T at b*128, dP^T at b*128+64
+constexpr int P_STAGE = P_DST0 + 2 * TILE128_BYTES;                          // two 16 KB tiles: gradients on their way out
+constexpr int PIPE_SMEM = P_STAGE + 2 * TILE128_BYTES + 1024;
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
-                     bf16* __restrict__ dqkv, int B, int T, int H, float scale) {
+                     const __grid_constant__ CUtensorMap map_dqkv, const bf16* __restrict__ out,
+                     const bf16* __restrict__ dout, const float* __restrict__ lse, int B, int T, int H, float scale) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
     __shared__ uint64_t d_full[2], d_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float lse2_s[2][KV_ROWS], dsum_s[2][KV_ROWS];     // per-query constants, double-buffered across heads
+    // per-query constants, double-buffered across heads: lse * log2(e) and scale * sum_d dO O
+    __shared__ __align__(16) float lse2_s[2][KV_ROWS], dsum_s[2][KV_ROWS];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NK = (T + 15) & ~15;
     const int items = B * H;
-    const int D3 = 3 * H * HD;
 
-    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_qkv); prefetch_tmap(&map_do); }
+    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_qkv); prefetch_tmap(&map_do); prefetch_tmap(&map_dqkv); }
     if (warp_idx == 1 && lane == 0) {
         mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&sd_full[b], 1); mbar_init(&tile_full[b], 16); mbar_init(&tile_free[b], 1); }
         mbar_init(&acc_full, 1); mbar_init(&acc_empty, 16); mbar_init(&dq_full, 1); mbar_init(&dq_empty, 16);
-        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], 16); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 2); mbar_init(&d_empty[b], 16); }
         fence_mbar_init();
     }
     if (warp_idx == 2) tmem_alloc(&tmem_slot, 512);
@@ -548,105 +640,132 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            const uint32_t sQ = smem_u32(smem + B_Q), sK = smem_u32(smem + B_K), sV = smem_u32(smem + B_V),
-                           sDO = smem_u32(smem + B_DO), sPT = smem_u32(smem + P_PT0), sDST = smem_u32(smem + P_DST0);
-            const uint32_t idesc_acc = make_idesc(128, HD, 0, 1);      // dV, dK: A K-major, B MN-major
-            const uint32_t idesc_dq = make_idesc(128, HD, 1, 1);       // dQ: A (dS^T buffers) MN-major, B MN-major
-            const uint32_t idesc_s64 = make_idesc(128, 64, 0, 0), idesc_s16 = make_idesc(128, 16, 0, 0);
-            // S^T = K_kt Q_qc^T and dP^T = V_kt dO_qc^T of chunk (kt, qc) into TMEM buffer qc & 1
-            auto issue_sd = [&](int kt, int qc) {
+        // The whole warp walks the (fully unrolled) schedule and waits; one elected lane issues.  The ~140 MMAs of a head
+        // are 16-32 tensor clocks each, so an issue must cost a few instructions: every descriptor is a precomputed base
+        // plus a compile-time offset (elect_one() in warp-uniform flow keeps them in uniform registers).
+        const uint32_t sQ = smem_u32(smem + B_Q), sK = smem_u32(smem + B_K), sV = smem_u32(smem + B_V),
+                       sDO = smem_u32(smem + B_DO), sPT = smem_u32(smem + P_PT0), sDST = smem_u32(smem + P_DST0);
+        const uint32_t idesc_acc = make_idesc(128, HD, 0, 1);      // dV, dK: A K-major, B MN-major
+        const uint32_t idesc_dq = make_idesc(128, HD, 1, 1);       // dQ: A (dS^T buffers) MN-major, B MN-major
+        const uint32_t idesc_s64 = make_idesc(128, 64, 0, 0), idesc_s16 = make_idesc(128, 16, 0, 0);
+        const uint64_t kK = make_desc(sK, 16, 1024), kQ = make_desc(sQ, 16, 1024), kV = make_desc(sV, 16, 1024),
+                       kDO = make_desc(sDO, 16, 1024), kPT = make_desc(sPT, 16, 1024), kDST = make_desc(sDST, 16, 1024);
+        const uint64_t mDO = make_desc(sDO, 8192, 1024), mQ = make_desc(sQ, 8192, 1024), mK = make_desc(sK, 8192, 1024),
+                       mDST = make_desc(sDST, TILE128_BYTES, 1024);
+        // S^T = K_kt Q_qc^T and dP^T = V_kt dO_qc^T of chunk (kt, qc) into TMEM buffer qc & 1
+        auto issue_sd = [&](int kt, int qc) {
+            if (elect_one()) {
                 const uint32_t tb = tmem + P_SD + (qc & 1) * 128;
                 const uint32_t id = qc == 3 ? idesc_s16 : idesc_s64;
                 // the two accumulation chains are interleaved: successive MMAs into one accumulator serialise on the
                 // tensor pipe's latency, which is what bounds these small (N <= 64) instructions
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
-                    tc_mma_f16(tb, make_desc(sK + kt * TILE128_BYTES + k * 32, 16, 1024),
-                               make_desc(sQ + qc * 8192 + k * 32, 16, 1024), id, k > 0);
-                    tc_mma_f16(tb + 64, make_desc(sV + kt * TILE128_BYTES + k * 32, 16, 1024),
-                               make_desc(sDO + qc * 8192 + k * 32, 16, 1024), id, k > 0);
+                    tc_mma_f16(tb, kK + (uint64_t)((kt * TILE128_BYTES + k * 32) >> 4), kQ + (uint64_t)((qc * 8192 + k * 32) >> 4),
+                               id, k > 0);
+                    tc_mma_f16(tb + 64, kV + (uint64_t)((kt * TILE128_BYTES + k * 32) >> 4),
+                               kDO + (uint64_t)((qc * 8192 + k * 32) >> 4), id, k > 0);
                 }
                 tc_commit(&sd_full[qc & 1]);
-            };
-            int it = 0;
-            uint32_t use[2] = {0, 0};      // completed uses of each buffer (phase of tile_full)
-            uint32_t ktg = 0;
-            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-                mbar_wait(&ops_full, it & 1);
-                mbar_wait(&dq_empty, (it & 1) ^ 1);
-                tc_fence_after();
-                issue_sd(0, 0);
-                for (int kt = 0; kt < 2; ++kt, ++ktg) {
-                    const int key_steps = (kt == 0 ? 128 : NK - 128) / 16;
-                    for (int qc = 0; qc < 4; ++qc) {
-                        const int b = qc & 1;
-                        // next chunk's S^T / dP^T: its TMEM buffer was read out before tile_full of the step two back
-                        if (qc < 3) issue_sd(kt, qc + 1);
-                        else if (kt == 0) issue_sd(1, 0);
-                        mbar_wait(&tile_full[b], use[b] & 1);
-                        ++use[b];
-                        tc_fence_after();
-                        if (qc == 0) {
-                            mbar_wait(&acc_empty, (ktg & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        const int q_steps = qc == 3 ? 1 : 4;
+            }
+            __syncwarp();
+        };
+        int it = 0;
+        uint32_t use[2] = {0, 0};      // completed uses of each buffer (phase of tile_full)
+        uint32_t ktg = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            mbar_wait(&ops_full, it & 1);
+            mbar_wait(&dq_empty, (it & 1) ^ 1);
+            tc_fence_after();
+            issue_sd(0, 0);
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const int key_steps = (kt == 0 ? 128 : NK - 128) / 16;
+#pragma unroll
+                for (int qc = 0; qc < 4; ++qc) {
+                    const int b = qc & 1;
+                    // next chunk's S^T / dP^T: its TMEM buffer was read out before tile_full of the step two back
+                    if (qc < 3) issue_sd(kt, qc + 1);
+                    else if (kt == 0) issue_sd(1, 0);
+                    mbar_wait(&tile_full[b], use[b] & 1);
+                    ++use[b];
+                    if (qc == 0) mbar_wait(&acc_empty, (ktg & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
                         // dV, dK (K = this chunk's queries) and, on the second chunk of a pair, dQ of the query tile the
                         // pair covers (the two dS^T buffers as one MN-major operand, K = this tile's keys): three
                         // independent accumulation chains, issued round-robin
-                        const int dq_steps = b == 1 ? key_steps : 0;
-                        for (int k = 0; k < (q_steps > dq_steps ? q_steps : dq_steps); ++k) {
-                            if (k < q_steps) {
-                                const uint64_t bdo = make_desc(sDO + qc * 8192 + k * 2048, 8192, 1024);
-                                const uint64_t bq = make_desc(sQ + qc * 8192 + k * 2048, 8192, 1024);
-                                tc_mma_f16(tmem + C_DV, make_desc(sPT + b * TILE128_BYTES + k * 32, 16, 1024), bdo, idesc_acc,
-                                           (qc > 0 || k > 0));
-                                tc_mma_f16(tmem + C_DK, make_desc(sDST + b * TILE128_BYTES + k * 32, 16, 1024), bq, idesc_acc,
-                                           (qc > 0 || k > 0));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (k < (qc == 3 ? 1 : 4)) {
+                                tc_mma_f16(tmem + C_DV, kPT + (uint64_t)((b * TILE128_BYTES + k * 32) >> 4),
+                                           mDO + (uint64_t)((qc * 8192 + k * 2048) >> 4), idesc_acc, (qc > 0 || k > 0));
+                                tc_mma_f16(tmem + C_DK, kDST + (uint64_t)((b * TILE128_BYTES + k * 32) >> 4),
+                                           mQ + (uint64_t)((qc * 8192 + k * 2048) >> 4), idesc_acc, (qc > 0 || k > 0));
                             }
-                            if (k < dq_steps)
-                                tc_mma_f16(tmem + C_DQ + (qc >> 1) * HD, make_desc(sDST + k * 2048, TILE128_BYTES, 1024),
-                                           make_desc(sK + kt * TILE128_BYTES + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0));
+                            if (b == 1 && k < key_steps)
+                                tc_mma_f16(tmem + C_DQ + (qc >> 1) * HD, mDST + (uint64_t)((k * 2048) >> 4),
+                                           mK + (uint64_t)((kt * TILE128_BYTES + k * 2048) >> 4), idesc_dq, (kt > 0 || k > 0));
                         }
                         if (b == 1) {
                             tc_commit(&tile_free[0]);
                             tc_commit(&tile_free[1]);
                         }
+                        if (qc == 3) {
+                            tc_commit(&acc_full);
+                            if (kt == 1) {
+                                tc_commit(&dq_full);
+                                tc_commit(&ops_empty);
+                            }
+                        }
                     }
-                    tc_commit(&acc_full);
+                    __syncwarp();
                 }
-                tc_commit(&dq_full);
-                tc_commit(&ops_empty);
+                ++ktg;
             }
         }
-    } else if (warp_idx == 3) {
-        // D[q] = sum_d dO[q,d] O[q,d] and lse[q] * log2(e) of the NEXT head while the other warps work on the current one
+    } else if (warp_idx < 4) {
+        // Warps 2 and 3: D[q] = scale * sum_d dO[q,d] O[q,d] and lse[q] * log2(e) of the NEXT head while the other warps work
+        // on the current one.  Each warp takes half of the rows, 8 lanes per row (one 128-byte line per row and tensor, four
+        // rows per load instruction) and 8 row groups in flight, so that a head costs four global-latency round trips
+        // instead of one per 32 rows with every lane on its own line.
+        const int hw = warp_idx - 2, sub = lane >> 3, c8 = lane & 7;
+        constexpr int ROWS_W = KV_ROWS / 2;                      // 104 rows per warp
         int it = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int b = w / H, h = w - b * H;
             const int buf = it & 1;
             mbar_wait(&d_empty[buf], ((it >> 1) & 1) ^ 1);
-            for (int q = lane; q < KV_ROWS; q += 32) {
-                float d = 0.f, l2 = 0.f;
-                if (q < T) {
-                    const long long off = ((long long)b * T + q) * (H * HD) + h * HD;
-                    bf16x8 vo[8], vg[8];
+            const long long base = (long long)b * T * (H * HD) + h * HD + c8 * 8;
+            for (int r0 = hw * ROWS_W; r0 < (hw + 1) * ROWS_W; r0 += 32) {
+                bf16x8 vo[8], vg[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { vo[k] = ld_global_v4(out + off + k * 8); vg[k] = ld_global_v4(dout + off + k * 8); }
+                for (int u = 0; u < 8; ++u) {
+                    const int q = r0 + u * 4 + sub;
+                    if (q < T && q < (hw + 1) * ROWS_W) {
+                        vo[u] = ld_global_v4(out + base + (long long)q * (H * HD));
+                        vg[u] = ld_global_v4(dout + base + (long long)q * (H * HD));
+                    }
+                }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                for (int u = 0; u < 8; ++u) {
+                    const int q = r0 + u * 4 + sub;
+                    float d = 0.f;
+                    if (q < T && q < (hw + 1) * ROWS_W) {
                         float fo[8], fg[8];
-                        unpack8(vo[k], fo);
-                        unpack8(vg[k], fg);
+                        unpack8(vo[u], fo);
+                        unpack8(vg[u], fg);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) d += fo[j] * fg[j];
                     }
-                    l2 = lse[((long long)b * H + h) * T + q] * LOG2E;
+                    d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    d += __shfl_xor_sync(0xffffffffu, d, 2);
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
+                    if (c8 == 0 && q < (hw + 1) * ROWS_W) dsum_s[buf][q] = d * scale;
                 }
-                dsum_s[buf][q] = d;
-                lse2_s[buf][q] = l2;
             }
+            for (int q = hw * ROWS_W + lane; q < (hw + 1) * ROWS_W; q += 32)
+                lse2_s[buf][q] = q < T ? lse[((long long)b * H + h) * T + q] * LOG2E : 0.f;
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_full[buf]);
         }
@@ -660,13 +779,20 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         const float sl2 = scale * LOG2E;
         const uint32_t sPT = smem_u32(smem + P_PT0) + row * 128;
         const uint32_t sDST = smem_u32(smem + P_DST0) + row * 128;
+        const bool storer = ew == 0 && lane == 0;            // issues the TMA stores of the staged gradient tiles
         int it = 0;
         uint32_t use[2] = {0, 0};
         uint32_t ktg = 0;
+#ifdef DFU_ATTN_TRACE
+        const bool trb = blockIdx.x == 0 && ew == 0 && lane == 0;
+        long long tprev = clock64();
+#endif
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int b = w / H, h = w - b * H;
             const int dbuf = it & 1;
+            ATTN_ACC(9);
             mbar_wait(&d_full[dbuf], (it >> 1) & 1);         // this head's per-query constants (written by warp 3)
+            ATTN_ACC(0);
             const float* lse2c = lse2_s[dbuf];
             const float* dsumc = dsum_s[dbuf];
             for (int kt = 0; kt < 2; ++kt, ++ktg) {
@@ -676,24 +802,44 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     const int bf = qc & 1;
                     mbar_wait(&sd_full[bf], use[bf] & 1);
                     tc_fence_after();
+                    ATTN_ACC(1);
                     const bool active = qc < 3 || cg == 0;        // the last chunk holds 16 queries
                     float p[16], ds[16];
                     if (active) {
                         uint32_t s[16], dp[16];
                         tmem_ld16(tlane + P_SD + bf * 128 + cg * 16, s);
                         tmem_ld16(tlane + P_SD + bf * 128 + 64 + cg * 16, dp);
-                        tmem_ld_wait();
+                        const int q0 = qc * 64 + cg * 16;
+                        float lq[16], dq[16];                     // the 16 queries' constants: 8 broadcast LDS.128
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int q = qc * 64 + cg * 16 + j;
-                            const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lse2c[q]);
-                            const bool ok = key_ok && (q < T);
-                            p[j] = ok ? e : 0.f;
-                            ds[j] = ok ? e * (__uint_as_float(dp[j]) - dsumc[q]) * scale : 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 l = *reinterpret_cast<const float4*>(lse2c + q0 + 4 * j);
+                            const float4 d = *reinterpret_cast<const float4*>(dsumc + q0 + 4 * j);
+                            lq[4 * j] = l.x; lq[4 * j + 1] = l.y; lq[4 * j + 2] = l.z; lq[4 * j + 3] = l.w;
+                            dq[4 * j] = d.x; dq[4 * j + 1] = d.y; dq[4 * j + 2] = d.z; dq[4 * j + 3] = d.w;
+                        }
+                        tmem_ld_wait();
+                        if (kt == 0 && q0 + 16 <= T) {            // every key and query of this thread's slice is real: no masks
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lq[j]);
+                                p[j] = e;
+                                ds[j] = e * (__uint_as_float(dp[j]) * scale - dq[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float e = ex2_approx(__uint_as_float(s[j]) * sl2 - lq[j]);
+                                const bool ok = key_ok && (q0 + j < T);
+                                p[j] = ok ? e : 0.f;
+                                ds[j] = ok ? e * (__uint_as_float(dp[j]) * scale - dq[j]) : 0.f;
+                            }
                         }
                     }
+                    ATTN_ACC(2);
                     // the MMAs of the pair that last used this smem buffer have finished reading it
                     mbar_wait(&tile_free[bf], (use[bf] & 1) ^ 1);
+                    ATTN_ACC(3);
                     ++use[bf];
                     if (active) {
 #pragma unroll
@@ -707,54 +853,76 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tile_full[bf]);
+                    ATTN_ACC(4);
                 }
                 mbar_wait(&acc_full, ktg & 1);
                 tc_fence_after();
+                ATTN_ACC(5);
+                // dV / dK of this key tile leave through shared memory and TMA: a thread owns one row, so direct global
+                // stores would touch 32 different lines per instruction (measured: 3 k clocks per tile).  Column group
+                // (which, half) stages 32 columns of dV (which 0) or dK (which 1); the TMA store clips the keys >= T.
                 {
-                    const int which = cg >> 1, half = cg & 1;      // which: 0 = dV, 1 = dK
-                    bf16* drow = dqkv + ((long long)b * T + key) * D3 + (which == 0 ? 2 * H : H) * HD + h * HD + half * 32;
+                    const int which = cg >> 1, half = cg & 1;
                     uint32_t r[32];
                     tmem_ld32(tlane + (which == 0 ? C_DV : C_DK) + half * 32, r);
                     tmem_ld_wait();
-                    if (key_ok) {
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
-                            st_global_v4(drow + gq * 8, pack8(v));
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[dbuf]);
-            mbar_wait(&dq_full, it & 1);
-            tc_fence_after();
-            {
-                const int qt = cg >> 1, half = cg & 1;
-                const int q = qt * 128 + row;
-                bf16* drow = dqkv + ((long long)b * T + q) * D3 + h * HD + half * 32;
-                uint32_t r[32];
-                tmem_ld32(tlane + C_DQ + qt * HD + half * 32, r);
-                tmem_ld_wait();
-                if (q < T) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty);   // the accumulators are free for the next key tile
+                    if (storer) bulk_wait_read0();            // the previous TMA stores have read the staging tiles
+                    named_bar_sync(1, 512);
+                    const uint32_t sST = smem_u32(smem + P_STAGE + which * TILE128_BYTES) + row * 128;
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
-                        st_global_v4(drow + gq * 8, pack8(v));
+                        st_shared_v4(sST + (((half * 4 + gq) ^ (row & 7)) << 4), pack8(v));
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 512);
+                    if (storer) {
+                        tma_store_3d(&map_dqkv, smem + P_STAGE, (2 * H + h) * HD, kt * 128, b);
+                        tma_store_3d(&map_dqkv, smem + P_STAGE + TILE128_BYTES, (H + h) * HD, kt * 128, b);
+                        bulk_commit();
                     }
                 }
+                ATTN_ACC(6);
             }
-            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&dq_empty);
+            if (lane == 0) mbar_arrive(&d_empty[dbuf]);
+            mbar_wait(&dq_full, it & 1);
+            tc_fence_after();
+            ATTN_ACC(7);
+            {
+                const int qt = cg >> 1, half = cg & 1;          // column group (qt, half): 32 columns of query tile qt
+                uint32_t r[32];
+                tmem_ld32(tlane + C_DQ + qt * HD + half * 32, r);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dq_empty);
+                if (storer) bulk_wait_read0();
+                named_bar_sync(1, 512);
+                const uint32_t sST = smem_u32(smem + P_STAGE + qt * TILE128_BYTES) + row * 128;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
+                    st_shared_v4(sST + (((half * 4 + gq) ^ (row & 7)) << 4), pack8(v));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 512);
+                if (storer) {
+                    tma_store_3d(&map_dqkv, smem + P_STAGE, h * HD, 0, b);
+                    tma_store_3d(&map_dqkv, smem + P_STAGE + TILE128_BYTES, h * HD, 128, b);
+                    bulk_commit();
+                }
+            }
+            ATTN_ACC(8);
         }
+        if (storer) bulk_wait0();                            // the last gradients are in global memory before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -781,10 +949,11 @@ extern "C" int dfu_attention_fwd(const void* qkv, void* out, float* lse, int32_t
     DFU_CHECK_ARG(qkv && out && lse, "dfu_attention_fwd: null pointer");
     if (int rc = check_shape("dfu_attention_fwd", B, T, H)) return rc;
     DFU_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "dfu_attention_fwd: unaligned buffers");
-    CUtensorMap map_q, map_kv;
+    CUtensorMap map_q, map_kv, map_o;
     const long long rows = (long long)B * T, cols = 3LL * H * HD;
     if (int rc = make_map_2d(&map_q, qkv, cols, rows, cols, HD, 128)) return rc;
     if (int rc = make_map_2d(&map_kv, qkv, cols, rows, cols, HD, KV_ROWS)) return rc;
+    if (int rc = make_map_3d(&map_o, out, (long long)H * HD, T, B, (long long)H * HD, HD, 128)) return rc;
     if (!g_attr_fwd) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
         if (e != cudaSuccess) {
@@ -796,7 +965,7 @@ extern "C" int dfu_attention_fwd(const void* qkv, void* out, float* lse, int32_t
     }
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
-    dfu_launch(attn_fwd_kernel, grid, THREADS, FWD_SMEM, (cudaStream_t)stream, map_q, map_kv, (bf16*)out, lse, B, T, H, scale);
+    dfu_launch(attn_fwd_kernel, grid, THREADS, FWD_SMEM, (cudaStream_t)stream, map_q, map_kv, map_o, lse, B, T, H, scale);
     DFU_CHECK_LAUNCH("attn_fwd_kernel");
     return DFU_OK;
 }
@@ -808,14 +977,15 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     DFU_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0 &&
                       ((uintptr_t)out & 3) == 0,
                   "dfu_attention_bwd: unaligned buffers");
-    CUtensorMap map_qkv, map_do;
+    CUtensorMap map_qkv, map_do, map_dqkv;
     const long long rows = (long long)B * T;
     if (int rc = make_map_2d(&map_qkv, qkv, 3LL * H * HD, rows, 3LL * H * HD, HD, KV_ROWS)) return rc;
     if (int rc = make_map_2d(&map_do, dout, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;
+    if (int rc = make_map_3d(&map_dqkv, dqkv, 3LL * H * HD, T, B, 3LL * H * HD, HD, 128)) return rc;
     if (!g_attr_bwd) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+            e = cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
         if (e != cudaSuccess) {
             dfu_set_error("dfu_attention_bwd: cannot reserve %d B shared memory: %s", BWD_SMEM, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -826,11 +996,18 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
     if (g_bwd_pipe)
-        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out,
-                                                                                (const bf16*)dout, lse, (bf16*)dqkv, B, T, H, scale);
+        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, PIPE_SMEM, (cudaStream_t)stream, map_qkv, map_do, map_dqkv, (const bf16*)out,
+                   (const bf16*)dout, lse, B, T, H, scale);
     else
         dfu_launch(attn_bwd_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
                                                                            lse, (bf16*)dqkv, B, T, H, scale);
     DFU_CHECK_LAUNCH("attn_bwd_kernel");
     return DFU_OK;
 }
+
+#ifdef DFU_ATTN_TRACE
+// Tracing build only (not declared in include/dfu_b200.h): copies CTA 0's phase clocks, 4 x 16 x 12 int64, to the host.
+extern "C" int dfu_attn_trace_read_host(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(g_attn_trace)) == cudaSuccess ? DFU_OK : DFU_ERR_CUDA;
+}
+#endif

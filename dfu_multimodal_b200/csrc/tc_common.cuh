@@ -66,6 +66,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
@@ -103,6 +109,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// One lane of a converged warp (the same one every time).  Code under `if (elect_one())` in otherwise warp-uniform control
+// flow lets ptxas keep descriptors in uniform registers and issue tcgen05.mma without the per-instruction vote / loop it
+// wraps around an MMA that sits in a `lane == 0` branch -- which matters when the MMAs are small (attention).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
@@ -197,6 +217,27 @@ inline int make_map_2d(CUtensorMap* map, const void* base, long long cols, long 
     if (r != CUDA_SUCCESS) {
         dfu_set_error("cuTensorMapEncodeTiled(2d) failed (%d): cols=%lld rows=%lld ld=%lld box=%dx%d", (int)r, cols, rows, ld,
                       box_cols, box_rows);
+        return DFU_ERR_CUDA;
+    }
+    return DFU_OK;
+}
+
+// 3-D bf16 tensor map {cols, rows, batch} over a [batch][rows][ld] matrix, box {box_cols, box_rows, 1}, SWIZZLE_128B: a box
+// that runs past `rows` is clipped (stores) / zero-filled (loads) instead of running into the next batch entry.
+inline int make_map_3d(CUtensorMap* map, const void* base, long long cols, long long rows, long long batch, long long ld,
+                       int box_cols, int box_rows) {
+    auto enc = get_encode();
+    if (!enc) { dfu_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DFU_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfu_set_error("cuTensorMapEncodeTiled(3d) failed (%d): cols=%lld rows=%lld batch=%lld ld=%lld box=%dx%d", (int)r, cols,
+                      rows, batch, ld, box_cols, box_rows);
         return DFU_ERR_CUDA;
     }
     return DFU_OK;
