@@ -54,7 +54,7 @@ __device__ long long g_attn_trace[4][16][12];
 #define ATTN_ACC(cat)                                                                           \
     do {                                                                                        \
         const long long now_ = clock64();                                                       \
-        if (trb) g_attn_trace[3][it < 15 ? it : 15][cat] += now_ - tprev;                        \
+        if (trb) tr_acc[cat] += now_ - tprev;     /* shared memory: a global read-modify-write would stall the warp */ \
         tprev = now_;                                                                           \
     } while (0)
 #else
@@ -585,20 +585,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 // per chunk and dQ per chunk PAIR (M = 128 queries, the two dS^T buffers read as one MN-major operand).
 constexpr int P_PT0 = 4 * KV_BYTES, P_DST0 = P_PT0 + 2 * TILE128_BYTES;      // PT[2] then DST[2], 16 KB each
 constexpr int P_SD = 0;                                                      // TMEM: buffer b -> S^T at b*128, dP^T at b*128+64
-constexpr int P_STAGE = P_DST0 + 2 * TILE128_BYTES;                          // two 16 KB tiles: gradients on their way out
-constexpr int PIPE_SMEM = P_STAGE + 2 * TILE128_BYTES + 1024;
+constexpr int P_O = P_DST0 + 2 * TILE128_BYTES;                              // O rows of the head (for D = rowsum(dO * O))
+constexpr int PIPE_SMEM = P_O + KV_BYTES + 1024;
+// Gradient tiles on their way out are staged in PT[1] / DST[1]: free from acc_full / dq_full (every MMA that read them has
+// completed) until the exp warps write chunk 1 of the next key tile, which first waits for the TMA store to have read them.
+constexpr int P_STAGE0 = P_PT0 + TILE128_BYTES, P_STAGE1 = P_DST0 + TILE128_BYTES;
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                     const __grid_constant__ CUtensorMap map_dqkv, const bf16* __restrict__ out,
+                     const __grid_constant__ CUtensorMap map_dqkv, const __grid_constant__ CUtensorMap map_out,
+                     const bf16* __restrict__ out,
                      const bf16* __restrict__ dout, const float* __restrict__ lse, int B, int T, int H, float scale) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
-    __shared__ uint64_t d_full[2], d_empty[2];
     __shared__ uint32_t tmem_slot;
-    // per-query constants, double-buffered across heads: lse * log2(e) and scale * sum_d dO O
-    __shared__ __align__(16) float lse2_s[2][KV_ROWS], dsum_s[2][KV_ROWS];
+    // per-query constants of the head: lse * log2(e) and D = scale * sum_d dO O
+    __shared__ __align__(16) float lse2_s[KV_ROWS], dsum_s[KV_ROWS];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NK = (T + 15) & ~15;
@@ -609,7 +612,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&sd_full[b], 1); mbar_init(&tile_full[b], 16); mbar_init(&tile_free[b], 1); }
         mbar_init(&acc_full, 1); mbar_init(&acc_empty, 16); mbar_init(&dq_full, 1); mbar_init(&dq_empty, 16);
-        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 2); mbar_init(&d_empty[b], 16); }
         fence_mbar_init();
     }
     if (warp_idx == 2) tmem_alloc(&tmem_slot, 512);
@@ -625,17 +627,19 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 const int b = w / H, h = w - b * H;
                 const int row0 = b * T;
                 mbar_wait(&ops_empty, (it & 1) ^ 1);
-                mbar_expect_tx(&ops_full, 4 * KV_BYTES);
+                mbar_expect_tx(&ops_full, 5 * KV_BYTES);
                 tma_load_2d(&map_qkv, &ops_full, smem + B_Q, h * HD, row0);
                 tma_load_2d(&map_qkv, &ops_full, smem + B_K, (H + h) * HD, row0);
                 tma_load_2d(&map_qkv, &ops_full, smem + B_V, (2 * H + h) * HD, row0);
                 tma_load_2d(&map_do, &ops_full, smem + B_DO, h * HD, row0);
+                tma_load_2d(&map_out, &ops_full, smem + P_O, h * HD, row0);
                 if (w + (int)gridDim.x < items) {
                     const int wn = w + gridDim.x, bn = wn / H, hn = wn - bn * H;
                     tma_prefetch_2d(&map_qkv, hn * HD, bn * T);
                     tma_prefetch_2d(&map_qkv, (H + hn) * HD, bn * T);
                     tma_prefetch_2d(&map_qkv, (2 * H + hn) * HD, bn * T);
                     tma_prefetch_2d(&map_do, hn * HD, bn * T);
+                    tma_prefetch_2d(&map_out, hn * HD, bn * T);
                 }
             }
         }
@@ -724,51 +728,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 ++ktg;
             }
         }
-    } else if (warp_idx < 4) {
-        // Warps 2 and 3: D[q] = scale * sum_d dO[q,d] O[q,d] and lse[q] * log2(e) of the NEXT head while the other warps work
-        // on the current one.  Each warp takes half of the rows, 8 lanes per row (one 128-byte line per row and tensor, four
-        // rows per load instruction) and 8 row groups in flight, so that a head costs four global-latency round trips
-        // instead of one per 32 rows with every lane on its own line.
-        const int hw = warp_idx - 2, sub = lane >> 3, c8 = lane & 7;
-        constexpr int ROWS_W = KV_ROWS / 2;                      // 104 rows per warp
-        int it = 0;
-        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-            const int b = w / H, h = w - b * H;
-            const int buf = it & 1;
-            mbar_wait(&d_empty[buf], ((it >> 1) & 1) ^ 1);
-            const long long base = (long long)b * T * (H * HD) + h * HD + c8 * 8;
-            for (int r0 = hw * ROWS_W; r0 < (hw + 1) * ROWS_W; r0 += 32) {
-                bf16x8 vo[8], vg[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int q = r0 + u * 4 + sub;
-                    if (q < T && q < (hw + 1) * ROWS_W) {
-                        vo[u] = ld_global_v4(out + base + (long long)q * (H * HD));
-                        vg[u] = ld_global_v4(dout + base + (long long)q * (H * HD));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int q = r0 + u * 4 + sub;
-                    float d = 0.f;
-                    if (q < T && q < (hw + 1) * ROWS_W) {
-                        float fo[8], fg[8];
-                        unpack8(vo[u], fo);
-                        unpack8(vg[u], fg);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) d += fo[j] * fg[j];
-                    }
-                    d += __shfl_xor_sync(0xffffffffu, d, 1);
-                    d += __shfl_xor_sync(0xffffffffu, d, 2);
-                    d += __shfl_xor_sync(0xffffffffu, d, 4);
-                    if (c8 == 0 && q < (hw + 1) * ROWS_W) dsum_s[buf][q] = d * scale;
-                }
-            }
-            for (int q = hw * ROWS_W + lane; q < (hw + 1) * ROWS_W; q += 32)
-                lse2_s[buf][q] = q < T ? lse[((long long)b * H + h) * T + q] * LOG2E : 0.f;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_full[buf]);
-        }
     } else if (warp_idx >= 4) {
         // 16 warps: warp (quarter, cg) owns TMEM lanes 32*quarter..+31 and 16 of the 64 query columns of each chunk
         const int ew = warp_idx - 4;
@@ -780,21 +739,54 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         const uint32_t sPT = smem_u32(smem + P_PT0) + row * 128;
         const uint32_t sDST = smem_u32(smem + P_DST0) + row * 128;
         const bool storer = ew == 0 && lane == 0;            // issues the TMA stores of the staged gradient tiles
+        const int tid = threadIdx.x - 128;                   // 0..511 among the exp warps
+        float lse_next = 0.f;                                // lse[tid] of the next head (0 for the padding rows)
+        if (tid < T && (int)blockIdx.x < items)
+            lse_next = __ldg(lse + (long long)blockIdx.x * T + tid);       // lse is [B*H][T] and w = b * H + h
         int it = 0;
         uint32_t use[2] = {0, 0};
         uint32_t ktg = 0;
+        [[maybe_unused]] const bool trb = blockIdx.x == 0 && ew == 0 && lane == 0;      // the tracing thread (tracing builds)
 #ifdef DFU_ATTN_TRACE
-        const bool trb = blockIdx.x == 0 && ew == 0 && lane == 0;
+        __shared__ long long tr_acc[12];
+        if (trb)
+            for (int c = 0; c < 12; ++c) tr_acc[c] = 0;
         long long tprev = clock64();
 #endif
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int b = w / H, h = w - b * H;
-            const int dbuf = it & 1;
             ATTN_ACC(9);
-            mbar_wait(&d_full[dbuf], (it >> 1) & 1);         // this head's per-query constants (written by warp 3)
+            // The head's per-query constants.  dO is in shared memory for the MMAs and O arrives with it, so D costs each of
+            // the 512 threads four 16-byte chunk pairs and three shuffles right after ops_full, while the first S^T / dP^T
+            // chunk is still in the tensor core.  (Two spare warps summing the rows from global memory -- or from shared
+            // memory, a row per lane -- took 3.5-20 k clocks per head next to sixteen polling warps, and the exp warps
+            // waited on them.)  lse is prefetched a head ahead into one register of the first 208 threads.
+            mbar_wait(&ops_full, it & 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = (tid >> 3) + 64 * i, c = tid & 7;
+                float d = 0.f;
+                if (q < T) {
+                    const uint32_t off = q * 128 + ((c ^ (q & 7)) << 4);
+                    const uint4 uo = *reinterpret_cast<const uint4*>(smem + P_O + off);
+                    const uint4 ug = *reinterpret_cast<const uint4*>(smem + B_DO + off);
+                    float fo[8], fg[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(&uo), fo);
+                    unpack8(*reinterpret_cast<const bf16x8*>(&ug), fg);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d += fo[e] * fg[e];
+                }
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if (c == 0 && q < KV_ROWS) dsum_s[q] = d * scale;
+            }
+            if (tid < KV_ROWS) lse2_s[tid] = lse_next * LOG2E;
+            named_bar_sync(1, 512);
+            if (tid < T && w + (int)gridDim.x < items) lse_next = __ldg(lse + (long long)(w + gridDim.x) * T + tid);
             ATTN_ACC(0);
-            const float* lse2c = lse2_s[dbuf];
-            const float* dsumc = dsum_s[dbuf];
+            const float* lse2c = lse2_s;
+            const float* dsumc = dsum_s;
             for (int kt = 0; kt < 2; ++kt, ++ktg) {
                 const int key = kt * 128 + row;
                 const bool key_ok = key < T;
@@ -841,6 +833,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     mbar_wait(&tile_free[bf], (use[bf] & 1) ^ 1);
                     ATTN_ACC(3);
                     ++use[bf];
+                    if (qc == 1) {                               // PT[1] / DST[1] doubled as the gradient staging tiles:
+                        if (storer) bulk_wait_read0();           // the TMA stores issued before this key tile have read them
+                        named_bar_sync(1, 512);
+                    }
                     if (active) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
@@ -869,9 +865,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty);   // the accumulators are free for the next key tile
-                    if (storer) bulk_wait_read0();            // the previous TMA stores have read the staging tiles
-                    named_bar_sync(1, 512);
-                    const uint32_t sST = smem_u32(smem + P_STAGE + which * TILE128_BYTES) + row * 128;
+                    const uint32_t sST = smem_u32(smem + (which == 0 ? P_STAGE0 : P_STAGE1)) + row * 128;
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
                         float v[8];
@@ -882,15 +876,13 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     fence_proxy_async_smem();
                     named_bar_sync(1, 512);
                     if (storer) {
-                        tma_store_3d(&map_dqkv, smem + P_STAGE, (2 * H + h) * HD, kt * 128, b);
-                        tma_store_3d(&map_dqkv, smem + P_STAGE + TILE128_BYTES, (H + h) * HD, kt * 128, b);
+                        tma_store_3d(&map_dqkv, smem + P_STAGE0, (2 * H + h) * HD, kt * 128, b);
+                        tma_store_3d(&map_dqkv, smem + P_STAGE1, (H + h) * HD, kt * 128, b);
                         bulk_commit();
                     }
                 }
                 ATTN_ACC(6);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[dbuf]);
             mbar_wait(&dq_full, it & 1);
             tc_fence_after();
             ATTN_ACC(7);
@@ -902,9 +894,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&dq_empty);
-                if (storer) bulk_wait_read0();
+                if (storer) bulk_wait_read0();                   // dV / dK of the second key tile have left the staging tiles
                 named_bar_sync(1, 512);
-                const uint32_t sST = smem_u32(smem + P_STAGE + qt * TILE128_BYTES) + row * 128;
+                const uint32_t sST = smem_u32(smem + (qt == 0 ? P_STAGE0 : P_STAGE1)) + row * 128;
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
                     float v[8];
@@ -915,12 +907,16 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 fence_proxy_async_smem();
                 named_bar_sync(1, 512);
                 if (storer) {
-                    tma_store_3d(&map_dqkv, smem + P_STAGE, h * HD, 0, b);
-                    tma_store_3d(&map_dqkv, smem + P_STAGE + TILE128_BYTES, h * HD, 128, b);
+                    tma_store_3d(&map_dqkv, smem + P_STAGE0, h * HD, 0, b);
+                    tma_store_3d(&map_dqkv, smem + P_STAGE1, h * HD, 128, b);
                     bulk_commit();
                 }
             }
             ATTN_ACC(8);
+#ifdef DFU_ATTN_TRACE
+            if (trb && it < 16)
+                for (int c = 0; c < 12; ++c) g_attn_trace[3][it][c] = tr_acc[c];     // running sums up to this head
+#endif
         }
         if (storer) bulk_wait0();                            // the last gradients are in global memory before the CTA retires
     }
@@ -975,13 +971,14 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     DFU_CHECK_ARG(qkv && out && dout && lse && dqkv, "dfu_attention_bwd: null pointer");
     if (int rc = check_shape("dfu_attention_bwd", B, T, H)) return rc;
     DFU_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0 &&
-                      ((uintptr_t)out & 3) == 0,
+                      ((uintptr_t)out & 15) == 0,
                   "dfu_attention_bwd: unaligned buffers");
-    CUtensorMap map_qkv, map_do, map_dqkv;
+    CUtensorMap map_qkv, map_do, map_dqkv, map_out;
     const long long rows = (long long)B * T;
     if (int rc = make_map_2d(&map_qkv, qkv, 3LL * H * HD, rows, 3LL * H * HD, HD, KV_ROWS)) return rc;
     if (int rc = make_map_2d(&map_do, dout, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;
     if (int rc = make_map_3d(&map_dqkv, dqkv, 3LL * H * HD, T, B, 3LL * H * HD, HD, 128)) return rc;
+    if (int rc = make_map_2d(&map_out, out, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;   // L2 prefetch only
     if (!g_attr_bwd) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
         if (e == cudaSuccess)
@@ -996,7 +993,7 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
     if (g_bwd_pipe)
-        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, PIPE_SMEM, (cudaStream_t)stream, map_qkv, map_do, map_dqkv, (const bf16*)out,
+        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, PIPE_SMEM, (cudaStream_t)stream, map_qkv, map_do, map_dqkv, map_out, (const bf16*)out,
                    (const bf16*)dout, lse, B, T, H, scale);
     else
         dfu_launch(attn_bwd_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out, (const bf16*)dout,

@@ -26,7 +26,7 @@ def build():
         obj = os.path.join(OUT, s.replace(".cu", ".o"))
         objs.append(obj)
         flags = [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-        procs.append(subprocess.Popen([B._nvcc()] + flags + ["-DDFU_ATTN_TRACE", "-c", os.path.join(B.CSRC, s), "-o", obj]))
+        procs.append(subprocess.Popen([B._nvcc()] + flags + ["-DDFU_ATTN_TRACE"] + os.environ.get("DFU_TRACE_DEFS", "").split() + ["-c", os.path.join(B.CSRC, s), "-o", obj]))
     if any(p.wait() for p in procs):
         raise SystemExit("nvcc failed")
     subprocess.check_call([B._nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
@@ -73,11 +73,10 @@ def main(B=128):
     print("attn_bwd B=%d: %.1f us per launch (5 back-to-back launches, tracing build)" % (B, ev[0].elapsed_time(ev[1]) * 200))
     buf = (ctypes.c_longlong * (4 * 16 * 12))()
     assert lib.dfu_attn_trace_read_host(buf) == 0
-    cats = ["wait d_full", "wait sd_full", "tmem ld + exp + dS", "wait tile_free", "write P^T/dS^T + arrive", "wait acc_full",
+    cats = ["ops_full + D", "wait sd_full", "tmem ld + exp + dS", "wait tile_free", "write P^T/dS^T + arrive", "wait acc_full",
             "dV/dK store", "wait dq_full", "dQ store", "loop"]
-    nb = 6      # launches accumulated
-    tot = [sum(buf[(3 * 16 + it) * 12 + c] for it in range(1, 9)) / (8.0 * nb) for c in range(10)]
-    print("backward, exp warp 0 of CTA 0, clocks per head (heads 1-8, mean of %d launches): total %.0f" % (nb, sum(tot)))
+    tot = [(buf[(3 * 16 + 8) * 12 + c] - buf[(3 * 16 + 0) * 12 + c]) / 8.0 for c in range(10)]      # running sums: heads 1..8
+    print("backward, exp warp 0 of CTA 0, clocks per head (heads 1-8 of the last launch): total %.0f" % sum(tot))
     print("  " + "  ".join("%s %.0f" % (n, v) for n, v in zip(cats, tot)))
     return
     t = [[[buf[(r * 16 + it) * 12 + p] for p in range(12)] for it in range(16)] for r in range(3)]
