@@ -587,8 +587,10 @@ constexpr int P_PT0 = 4 * KV_BYTES, P_DST0 = P_PT0 + 2 * TILE128_BYTES;      // 
 constexpr int P_SD = 0;                                                      // TMEM: buffer b -> S^T at b*128, dP^T at b*128+64
 constexpr int P_O = P_DST0 + 2 * TILE128_BYTES;                              // O rows of the head (for D = rowsum(dO * O))
 constexpr int PIPE_SMEM = P_O + KV_BYTES + 1024;
-// Gradient tiles on their way out are staged in PT[1] / DST[1]: free from acc_full / dq_full (every MMA that read them has
-// completed) until the exp warps write chunk 1 of the next key tile, which first waits for the TMA store to have read them.
+// Gradient tiles on their way out are staged in the P^T / dS^T operand tiles: dV / dK of a key tile in PT[1] / DST[1], dQ in
+// PT[0] / DST[0].  They are free from acc_full / dq_full (every MMA that read them has completed) until the exp warps write
+// that buffer again -- chunk 1 of the next key tile resp. chunk 0 of the next head -- which first waits for the TMA stores
+// to have read them.
 constexpr int P_STAGE0 = P_PT0 + TILE128_BYTES, P_STAGE1 = P_DST0 + TILE128_BYTES;
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -833,9 +835,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     mbar_wait(&tile_free[bf], (use[bf] & 1) ^ 1);
                     ATTN_ACC(3);
                     ++use[bf];
-                    if (qc == 1) {                               // PT[1] / DST[1] doubled as the gradient staging tiles:
-                        if (storer) bulk_wait_read0();           // the TMA stores issued before this key tile have read them
-                        named_bar_sync(1, 512);
+                    if (qc == kt) {                              // the tiles about to be written doubled as gradient staging
+                        if (storer) bulk_wait_read0();           // (dQ in PT[0] / DST[0], dV / dK in PT[1] / DST[1]): the TMA
+                        named_bar_sync(1, 512);                  // stores issued since have read them
                     }
                     if (active) {
 #pragma unroll
@@ -894,9 +896,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&dq_empty);
-                if (storer) bulk_wait_read0();                   // dV / dK of the second key tile have left the staging tiles
-                named_bar_sync(1, 512);
-                const uint32_t sST = smem_u32(smem + (qt == 0 ? P_STAGE0 : P_STAGE1)) + row * 128;
+                const uint32_t sST = smem_u32(smem + (qt == 0 ? P_PT0 : P_DST0)) + row * 128;
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
                     float v[8];
@@ -907,8 +907,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 fence_proxy_async_smem();
                 named_bar_sync(1, 512);
                 if (storer) {
-                    tma_store_3d(&map_dqkv, smem + P_STAGE0, h * HD, 0, b);
-                    tma_store_3d(&map_dqkv, smem + P_STAGE1, h * HD, 128, b);
+                    tma_store_3d(&map_dqkv, smem + P_PT0, h * HD, 0, b);
+                    tma_store_3d(&map_dqkv, smem + P_DST0, h * HD, 128, b);
                     bulk_commit();
                 }
             }
