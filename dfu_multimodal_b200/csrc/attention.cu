@@ -215,22 +215,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             // pass 1: row maximum of the raw scores (the next chunk's TMEM load is in flight while this one is reduced;
             // four independent chains so that the reduction is not one 104-deep dependency)
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            tmem_ld32(taddr + half * 32, ra);
+            // tcgen05.wait::ld waits for every outstanding load, so "load the next chunk while this one is reduced" leaves the
+            // ~300-clock TMEM latency exposed once per chunk (the reduction is 32 FMNMX).  Two chunks per round trip instead.
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 4; cc += 2) {
                 if (cc < my_chunks) {
-                    const int c = half + 2 * cc;
-                    uint32_t* cur = (cc & 1) ? rb : ra;
-                    uint32_t* nxt = (cc & 1) ? ra : rb;
+                    tmem_ld32(taddr + (half + 2 * cc) * 32, ra);
+                    if (cc + 1 < my_chunks) tmem_ld32(taddr + (half + 2 * cc + 2) * 32, rb);
                     tmem_ld_wait();
-                    if (cc + 1 < my_chunks) tmem_ld32(taddr + (c + 2) * 32, nxt);
-                    if (c * 32 + 32 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
-                    } else {
+                    for (int u = 0; u < 2; ++u) {
+                        if (cc + u < my_chunks) {
+                            const int c = half + 2 * (cc + u);
+                            const uint32_t* cur = u ? rb : ra;
+                            if (c * 32 + 32 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
+                                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (c * 32 + j < T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
+                            }
+                        }
                     }
                 }
             }
@@ -261,11 +267,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                             float p[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                p[j] = ex2_approx(__uint_as_float(cur[g * 8 + j]) * sl2 - ms);
+                                const float x = __uint_as_float(cur[g * 8 + j]) * sl2 - ms;
+#if defined(DFU_ATTN_EXP_NONE)      // timing experiment of tools/gpu_attn_trace.py (wrong results): the pass without the SFU
+                                p[j] = x * 0.5f;
+#else
+                                p[j] = ex2_approx(x);
+#endif
                                 s4[j & 3] += p[j];
                             }
                             const int atom = col0 >> 6, cj = (col0 & 63) >> 3;
+#ifndef DFU_ATTN_NO_PSTORE
                             st_shared_v4(sP + atom * TILE128_BYTES + ((cj ^ (row & 7)) << 4), pack8(p));
+#endif
                         }
                     } else {
 #pragma unroll

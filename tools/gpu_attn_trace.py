@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_build")
-LIB = os.path.join(OUT, "libdfu_b200_trace.so")
+LIB = os.environ.get("DFU_TRACE_LIB") or os.path.join(OUT, "libdfu_b200_trace.so")
 
 
 def build():
@@ -78,7 +78,6 @@ def main(B=128):
     tot = [(buf[(3 * 16 + 8) * 12 + c] - buf[(3 * 16 + 0) * 12 + c]) / 8.0 for c in range(10)]      # running sums: heads 1..8
     print("backward, exp warp 0 of CTA 0, clocks per head (heads 1-8 of the last launch): total %.0f" % sum(tot))
     print("  " + "  ".join("%s %.0f" % (n, v) for n, v in zip(cats, tot)))
-    return
     t = [[[buf[(r * 16 + it) * 12 + p] for p in range(12)] for it in range(16)] for r in range(3)]
     its = min(16, (B * H + 147) // 148)
     t0 = t[0][0][0]
