@@ -599,21 +599,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 constexpr int P_PT0 = 4 * KV_BYTES, P_DST0 = P_PT0 + 2 * TILE128_BYTES;      // PT[2] then DST[2], 16 KB each
 constexpr int P_SD = 0;                                                      // TMEM: buffer b -> S^T at b*128, dP^T at b*128+64
 constexpr int P_O = P_DST0 + 2 * TILE128_BYTES;                              // O rows of the head (for D = rowsum(dO * O))
-constexpr int PIPE_SMEM = P_O + KV_BYTES + 1024;
+// second home of the rows 0..63 of Q / dO / O (8 KB each): odd heads of a CTA keep their first query chunk here, so that it
+// can be loaded a head ahead while the previous head still uses rows 0..63 of B_Q / B_DO / P_O
+constexpr int P_XQ = P_O + KV_BYTES, P_XDO = P_XQ + 64 * 128, P_XO = P_XDO + 64 * 128;
+constexpr int PIPE_SMEM = P_XO + 64 * 128 + 1024;
 // Gradient tiles on their way out are staged in the P^T / dS^T operand tiles: dV / dK of a key tile in PT[1] / DST[1], dQ in
 // PT[0] / DST[0].  They are free from acc_full / dq_full (every MMA that read them has completed) until the exp warps write
 // that buffer again -- chunk 1 of the next key tile resp. chunk 0 of the next head -- which first waits for the TMA stores
 // to have read them.
 constexpr int P_STAGE0 = P_PT0 + TILE128_BYTES, P_STAGE1 = P_DST0 + TILE128_BYTES;
 
+// TMA views of the pipelined backward: loads of qkv / dO / O in boxes of 64, 144, 128 and 80 rows (the order the operands are
+// needed in), the clipped 3-D store view of dqkv.
+struct BwdMaps {
+    CUtensorMap qkv_64, qkv_144, qkv_128, qkv_80, do_64, do_144, out_64, out_144, dqkv;
+};
+
 __global__ void __launch_bounds__(THREADS, 1)
-attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                     const __grid_constant__ CUtensorMap map_dqkv, const __grid_constant__ CUtensorMap map_out,
-                     const bf16* __restrict__ out,
-                     const bf16* __restrict__ dout, const float* __restrict__ lse, int B, int T, int H, float scale) {
+attn_bwd_pipe_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ lse, int B, int T, int H, float scale) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t ops_full, ops_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty, dq_full, dq_empty;
+    __shared__ uint64_t full_a, full_b, full_kv0, ops_empty, kv0_empty, sd_full[2], tile_full[2], tile_free[2], acc_full, acc_empty,
+        dq_full, dq_empty;
     __shared__ uint32_t tmem_slot;
     // per-query constants of the head: lse * log2(e) and D = scale * sum_d dO O
     __shared__ __align__(16) float lse2_s[KV_ROWS], dsum_s[KV_ROWS];
@@ -622,9 +629,14 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     const int NK = (T + 15) & ~15;
     const int items = B * H;
 
-    if (warp_idx == 0 && lane == 0) { prefetch_tmap(&map_qkv); prefetch_tmap(&map_do); prefetch_tmap(&map_dqkv); }
+    if (warp_idx == 0 && lane == 0) {
+        prefetch_tmap(&maps.qkv_64); prefetch_tmap(&maps.qkv_144); prefetch_tmap(&maps.qkv_128); prefetch_tmap(&maps.qkv_80);
+        prefetch_tmap(&maps.do_64); prefetch_tmap(&maps.do_144); prefetch_tmap(&maps.out_64); prefetch_tmap(&maps.out_144);
+        prefetch_tmap(&maps.dqkv);
+    }
     if (warp_idx == 1 && lane == 0) {
-        mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
+        mbar_init(&full_a, 1); mbar_init(&full_b, 1); mbar_init(&full_kv0, 1);
+        mbar_init(&ops_empty, 1); mbar_init(&kv0_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&sd_full[b], 1); mbar_init(&tile_full[b], 16); mbar_init(&tile_free[b], 1); }
         mbar_init(&acc_full, 1); mbar_init(&acc_empty, 16); mbar_init(&dq_full, 1); mbar_init(&dq_empty, 16);
         fence_mbar_init();
@@ -637,24 +649,65 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 
     if (warp_idx == 0) {
         if (lane == 0) {
+            // The 133 KB of a head's operands arrive in the order they are needed, on three barriers, and as early as their
+            // buffers allow:
+            //   kv0  K and V of key tile 0 -- dead once the tile-0 MMAs have completed (kv0_empty), so the NEXT head's are
+            //        loaded half a head early, under this head's second key tile
+            //   a    Q / dO / O rows 0..63: with kv0, all the first chunk needs.  Two homes (in place for even heads, P_X* for
+            //        odd ones), so the next head's are loaded half a head early too
+            //   b    the rest (Q / dO / O rows 64.., K and V of key tile 1), once the previous head has completed; it lands
+            //        while the first chunk is being processed.  (One barrier per query chunk instead was slower: 142.7 vs
+            //        139.1 us per layer -- more, smaller TMA requests and three more CTA-wide barriers.)
+            // With one barrier for everything the exp warps idled ~5 k clocks of a ~22 k-clock head at every head boundary.
+            auto load_kv0 = [&](int w) {
+                const int b = w / H, h = w - b * H;
+                mbar_expect_tx(&full_kv0, 2 * TILE128_BYTES);
+                tma_load_2d(&maps.qkv_128, &full_kv0, smem + B_K, (H + h) * HD, b * T);
+                tma_load_2d(&maps.qkv_128, &full_kv0, smem + B_V, (2 * H + h) * HD, b * T);
+            };
+            auto load_a = [&](int w, int par) {
+                const int b = w / H, h = w - b * H;
+                mbar_expect_tx(&full_a, 3 * 64 * 128);
+                tma_load_2d(&maps.qkv_64, &full_a, smem + (par ? P_XQ : B_Q), h * HD, b * T);
+                tma_load_2d(&maps.do_64, &full_a, smem + (par ? P_XDO : B_DO), h * HD, b * T);
+                tma_load_2d(&maps.out_64, &full_a, smem + (par ? P_XO : P_O), h * HD, b * T);
+            };
+            if ((int)blockIdx.x < items) {
+                load_kv0(blockIdx.x);
+                load_a(blockIdx.x, 0);
+            }
             int it = 0;
             for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
                 const int b = w / H, h = w - b * H;
                 const int row0 = b * T;
+                const bool more = w + (int)gridDim.x < items;
                 mbar_wait(&ops_empty, (it & 1) ^ 1);
-                mbar_expect_tx(&ops_full, 5 * KV_BYTES);
-                tma_load_2d(&map_qkv, &ops_full, smem + B_Q, h * HD, row0);
-                tma_load_2d(&map_qkv, &ops_full, smem + B_K, (H + h) * HD, row0);
-                tma_load_2d(&map_qkv, &ops_full, smem + B_V, (2 * H + h) * HD, row0);
-                tma_load_2d(&map_do, &ops_full, smem + B_DO, h * HD, row0);
-                tma_load_2d(&map_out, &ops_full, smem + P_O, h * HD, row0);
-                if (w + (int)gridDim.x < items) {
-                    const int wn = w + gridDim.x, bn = wn / H, hn = wn - bn * H;
-                    tma_prefetch_2d(&map_qkv, hn * HD, bn * T);
-                    tma_prefetch_2d(&map_qkv, (H + hn) * HD, bn * T);
-                    tma_prefetch_2d(&map_qkv, (2 * H + hn) * HD, bn * T);
-                    tma_prefetch_2d(&map_do, hn * HD, bn * T);
-                    tma_prefetch_2d(&map_out, hn * HD, bn * T);
+                mbar_expect_tx(&full_b, 3 * 144 * 128 + 2 * 80 * 128);
+                tma_load_2d(&maps.qkv_144, &full_b, smem + B_Q + 64 * 128, h * HD, row0 + 64);
+                tma_load_2d(&maps.do_144, &full_b, smem + B_DO + 64 * 128, h * HD, row0 + 64);
+                tma_load_2d(&maps.out_144, &full_b, smem + P_O + 64 * 128, h * HD, row0 + 64);
+                tma_load_2d(&maps.qkv_80, &full_b, smem + B_K + TILE128_BYTES, (H + h) * HD, row0 + 128);
+                tma_load_2d(&maps.qkv_80, &full_b, smem + B_V + TILE128_BYTES, (2 * H + h) * HD, row0 + 128);
+                if (w + 2 * (int)gridDim.x < items) {            // the head after next -> L2
+                    const int wn = w + 2 * gridDim.x, bn = wn / H, hn = wn - bn * H;
+                    tma_prefetch_2d(&maps.qkv_64, hn * HD, bn * T);
+                    tma_prefetch_2d(&maps.qkv_144, hn * HD, bn * T + 64);
+                    tma_prefetch_2d(&maps.qkv_128, (H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&maps.qkv_80, (H + hn) * HD, bn * T + 128);
+                    tma_prefetch_2d(&maps.qkv_128, (2 * H + hn) * HD, bn * T);
+                    tma_prefetch_2d(&maps.qkv_80, (2 * H + hn) * HD, bn * T + 128);
+                    tma_prefetch_2d(&maps.do_64, hn * HD, bn * T);
+                    tma_prefetch_2d(&maps.do_144, hn * HD, bn * T + 64);
+                    tma_prefetch_2d(&maps.out_64, hn * HD, bn * T);
+                    tma_prefetch_2d(&maps.out_144, hn * HD, bn * T + 64);
+                }
+                if (more) {
+                    // This head's tile-0 MMAs have completed: K / V rows 0..127 are dead, and every consumer has passed its
+                    // wait on this head's phase of full_a / full_kv0 -- re-arming a barrier before its waiters have seen the
+                    // phase complete would let two phases go by and leave them waiting for the wrong parity.
+                    mbar_wait(&kv0_empty, it & 1);
+                    load_kv0(w + gridDim.x);
+                    load_a(w + gridDim.x, (it + 1) & 1);         // its home was last used by the head before this one
                 }
             }
         }
@@ -671,6 +724,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                        kDO = make_desc(sDO, 16, 1024), kPT = make_desc(sPT, 16, 1024), kDST = make_desc(sDST, 16, 1024);
         const uint64_t mDO = make_desc(sDO, 8192, 1024), mQ = make_desc(sQ, 8192, 1024), mK = make_desc(sK, 8192, 1024),
                        mDST = make_desc(sDST, TILE128_BYTES, 1024);
+        // the first query chunk of odd heads lives in P_XQ / P_XDO
+        const uint64_t kXQ = make_desc(smem_u32(smem + P_XQ), 16, 1024), kXDO = make_desc(smem_u32(smem + P_XDO), 16, 1024),
+                       mXQ = make_desc(smem_u32(smem + P_XQ), 8192, 1024), mXDO = make_desc(smem_u32(smem + P_XDO), 8192, 1024);
+        uint64_t kQ0 = kQ, kDO0 = kDO, mQ0 = mQ, mDO0 = mDO;      // this head's chunk-0 bases
         // S^T = K_kt Q_qc^T and dP^T = V_kt dO_qc^T of chunk (kt, qc) into TMEM buffer qc & 1
         auto issue_sd = [&](int kt, int qc) {
             if (elect_one()) {
@@ -680,10 +737,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 // tensor pipe's latency, which is what bounds these small (N <= 64) instructions
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
-                    tc_mma_f16(tb, kK + (uint64_t)((kt * TILE128_BYTES + k * 32) >> 4), kQ + (uint64_t)((qc * 8192 + k * 32) >> 4),
-                               id, k > 0);
+                    tc_mma_f16(tb, kK + (uint64_t)((kt * TILE128_BYTES + k * 32) >> 4),
+                               (qc == 0 ? kQ0 : kQ + (uint64_t)((qc * 8192) >> 4)) + (uint64_t)((k * 32) >> 4), id, k > 0);
                     tc_mma_f16(tb + 64, kV + (uint64_t)((kt * TILE128_BYTES + k * 32) >> 4),
-                               kDO + (uint64_t)((qc * 8192 + k * 32) >> 4), id, k > 0);
+                               (qc == 0 ? kDO0 : kDO + (uint64_t)((qc * 8192) >> 4)) + (uint64_t)((k * 32) >> 4), id, k > 0);
                 }
                 tc_commit(&sd_full[qc & 1]);
             }
@@ -693,10 +750,14 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         uint32_t use[2] = {0, 0};      // completed uses of each buffer (phase of tile_full)
         uint32_t ktg = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-            mbar_wait(&ops_full, it & 1);
+            kQ0 = (it & 1) ? kXQ : kQ; kDO0 = (it & 1) ? kXDO : kDO; mQ0 = (it & 1) ? mXQ : mQ; mDO0 = (it & 1) ? mXDO : mDO;
+            mbar_wait(&full_kv0, it & 1);
+            mbar_wait(&full_a, it & 1);
             mbar_wait(&dq_empty, (it & 1) ^ 1);
             tc_fence_after();
             issue_sd(0, 0);
+            mbar_wait(&full_b, it & 1);                          // everything after the first chunk needs the rest
+            tc_fence_after();
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) {
                 const int key_steps = (kt == 0 ? 128 : NK - 128) / 16;
@@ -718,9 +779,11 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                         for (int k = 0; k < 8; ++k) {
                             if (k < (qc == 3 ? 1 : 4)) {
                                 tc_mma_f16(tmem + C_DV, kPT + (uint64_t)((b * TILE128_BYTES + k * 32) >> 4),
-                                           mDO + (uint64_t)((qc * 8192 + k * 2048) >> 4), idesc_acc, (qc > 0 || k > 0));
+                                           (qc == 0 ? mDO0 : mDO + (uint64_t)((qc * 8192) >> 4)) + (uint64_t)((k * 2048) >> 4),
+                                           idesc_acc, (qc > 0 || k > 0));
                                 tc_mma_f16(tmem + C_DK, kDST + (uint64_t)((b * TILE128_BYTES + k * 32) >> 4),
-                                           mQ + (uint64_t)((qc * 8192 + k * 2048) >> 4), idesc_acc, (qc > 0 || k > 0));
+                                           (qc == 0 ? mQ0 : mQ + (uint64_t)((qc * 8192) >> 4)) + (uint64_t)((k * 2048) >> 4),
+                                           idesc_acc, (qc > 0 || k > 0));
                             }
                             if (b == 1 && k < key_steps)
                                 tc_mma_f16(tmem + C_DQ + (qc >> 1) * HD, mDST + (uint64_t)((k * 2048) >> 4),
@@ -732,6 +795,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                         }
                         if (qc == 3) {
                             tc_commit(&acc_full);
+                            if (kt == 0) tc_commit(&kv0_empty);      // K / V rows 0..127 are dead: the next head's may land
                             if (kt == 1) {
                                 tc_commit(&dq_full);
                                 tc_commit(&ops_empty);
@@ -772,19 +836,18 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             const int b = w / H, h = w - b * H;
             ATTN_ACC(9);
             // The head's per-query constants.  dO is in shared memory for the MMAs and O arrives with it, so D costs each of
-            // the 512 threads four 16-byte chunk pairs and three shuffles right after ops_full, while the first S^T / dP^T
-            // chunk is still in the tensor core.  (Two spare warps summing the rows from global memory -- or from shared
-            // memory, a row per lane -- took 3.5-20 k clocks per head next to sixteen polling warps, and the exp warps
-            // waited on them.)  lse is prefetched a head ahead into one register of the first 208 threads.
-            mbar_wait(&ops_full, it & 1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int q = (tid >> 3) + 64 * i, c = tid & 7;
+            // the 512 threads a few 16-byte chunk pairs and three shuffles: rows 0..63 as soon as barrier `a` fires (the
+            // first S^T / dP^T chunk is still in the tensor core), the rest before the second chunk.  (Two spare warps
+            // summing the rows from global memory -- or from shared memory, a row per lane -- took 3.5-20 k clocks per head
+            // next to sixteen polling warps, and the exp warps waited on them.)  lse is prefetched a head ahead into one
+            // register of the first 208 threads.
+            auto d_rows = [&](int q, const uint8_t* so, const uint8_t* sg) {      // 8 lanes per row
+                const int c = tid & 7;
                 float d = 0.f;
                 if (q < T) {
                     const uint32_t off = q * 128 + ((c ^ (q & 7)) << 4);
-                    const uint4 uo = *reinterpret_cast<const uint4*>(smem + P_O + off);
-                    const uint4 ug = *reinterpret_cast<const uint4*>(smem + B_DO + off);
+                    const uint4 uo = *reinterpret_cast<const uint4*>(so + off);
+                    const uint4 ug = *reinterpret_cast<const uint4*>(sg + off);
                     float fo[8], fg[8];
                     unpack8(*reinterpret_cast<const bf16x8*>(&uo), fo);
                     unpack8(*reinterpret_cast<const bf16x8*>(&ug), fg);
@@ -795,7 +858,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 d += __shfl_xor_sync(0xffffffffu, d, 2);
                 d += __shfl_xor_sync(0xffffffffu, d, 4);
                 if (c == 0 && q < KV_ROWS) dsum_s[q] = d * scale;
-            }
+            };
+            mbar_wait(&full_a, it & 1);
+            d_rows(tid >> 3, smem + ((it & 1) ? P_XO : P_O), smem + ((it & 1) ? P_XDO : B_DO));
             if (tid < KV_ROWS) lse2_s[tid] = lse_next * LOG2E;
             named_bar_sync(1, 512);
             if (tid < T && w + (int)gridDim.x < items) lse_next = __ldg(lse + (long long)(w + gridDim.x) * T + tid);
@@ -807,6 +872,12 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 const bool key_ok = key < T;
                 for (int qc = 0; qc < 4; ++qc) {
                     const int bf = qc & 1;
+                    if (kt == 0 && qc == 1) {                    // D of the queries 64.. (their rows came with barrier `b`)
+                        mbar_wait(&full_b, it & 1);
+#pragma unroll
+                        for (int i = 1; i < 4; ++i) d_rows((tid >> 3) + 64 * i, smem + P_O, smem + B_DO);
+                        named_bar_sync(1, 512);
+                    }
                     mbar_wait(&sd_full[bf], use[bf] & 1);
                     tc_fence_after();
                     ATTN_ACC(1);
@@ -891,8 +962,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                     fence_proxy_async_smem();
                     named_bar_sync(1, 512);
                     if (storer) {
-                        tma_store_3d(&map_dqkv, smem + P_STAGE0, (2 * H + h) * HD, kt * 128, b);
-                        tma_store_3d(&map_dqkv, smem + P_STAGE1, (H + h) * HD, kt * 128, b);
+                        tma_store_3d(&maps.dqkv, smem + P_STAGE0, (2 * H + h) * HD, kt * 128, b);
+                        tma_store_3d(&maps.dqkv, smem + P_STAGE1, (H + h) * HD, kt * 128, b);
                         bulk_commit();
                     }
                 }
@@ -920,8 +991,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 fence_proxy_async_smem();
                 named_bar_sync(1, 512);
                 if (storer) {
-                    tma_store_3d(&map_dqkv, smem + P_PT0, h * HD, 0, b);
-                    tma_store_3d(&map_dqkv, smem + P_DST0, h * HD, 128, b);
+                    tma_store_3d(&maps.dqkv, smem + P_PT0, h * HD, 0, b);
+                    tma_store_3d(&maps.dqkv, smem + P_DST0, h * HD, 128, b);
                     bulk_commit();
                 }
             }
@@ -986,12 +1057,23 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     DFU_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0 &&
                       ((uintptr_t)out & 15) == 0,
                   "dfu_attention_bwd: unaligned buffers");
-    CUtensorMap map_qkv, map_do, map_dqkv, map_out;
-    const long long rows = (long long)B * T;
-    if (int rc = make_map_2d(&map_qkv, qkv, 3LL * H * HD, rows, 3LL * H * HD, HD, KV_ROWS)) return rc;
-    if (int rc = make_map_2d(&map_do, dout, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;
-    if (int rc = make_map_3d(&map_dqkv, dqkv, 3LL * H * HD, T, B, 3LL * H * HD, HD, 128)) return rc;
-    if (int rc = make_map_2d(&map_out, out, (long long)H * HD, rows, (long long)H * HD, HD, KV_ROWS)) return rc;   // L2 prefetch only
+    const long long rows = (long long)B * T, c3 = 3LL * H * HD, c1 = (long long)H * HD;
+    CUtensorMap map_qkv, map_do;                                 // serial kernel: whole-head boxes
+    BwdMaps maps;
+    if (g_bwd_pipe) {
+        if (int rc = make_map_2d(&maps.qkv_64, qkv, c3, rows, c3, HD, 64)) return rc;
+        if (int rc = make_map_2d(&maps.qkv_144, qkv, c3, rows, c3, HD, KV_ROWS - 64)) return rc;
+        if (int rc = make_map_2d(&maps.qkv_128, qkv, c3, rows, c3, HD, 128)) return rc;
+        if (int rc = make_map_2d(&maps.qkv_80, qkv, c3, rows, c3, HD, KV_ROWS - 128)) return rc;
+        if (int rc = make_map_2d(&maps.do_64, dout, c1, rows, c1, HD, 64)) return rc;
+        if (int rc = make_map_2d(&maps.do_144, dout, c1, rows, c1, HD, KV_ROWS - 64)) return rc;
+        if (int rc = make_map_2d(&maps.out_64, out, c1, rows, c1, HD, 64)) return rc;
+        if (int rc = make_map_2d(&maps.out_144, out, c1, rows, c1, HD, KV_ROWS - 64)) return rc;
+        if (int rc = make_map_3d(&maps.dqkv, dqkv, c3, T, B, c3, HD, 128)) return rc;
+    } else {
+        if (int rc = make_map_2d(&map_qkv, qkv, c3, rows, c3, HD, KV_ROWS)) return rc;
+        if (int rc = make_map_2d(&map_do, dout, c1, rows, c1, HD, KV_ROWS)) return rc;
+    }
     if (!g_attr_bwd) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
         if (e == cudaSuccess)
@@ -1006,8 +1088,7 @@ extern "C" int dfu_attention_bwd(const void* qkv, const void* out, const void* d
     const int items = B * H;
     const int grid = items < dfu_num_sms() ? items : dfu_num_sms();
     if (g_bwd_pipe)
-        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, PIPE_SMEM, (cudaStream_t)stream, map_qkv, map_do, map_dqkv, map_out, (const bf16*)out,
-                   (const bf16*)dout, lse, B, T, H, scale);
+        dfu_launch(attn_bwd_pipe_kernel, grid, THREADS, PIPE_SMEM, (cudaStream_t)stream, maps, lse, B, T, H, scale);
     else
         dfu_launch(attn_bwd_kernel, grid, THREADS, BWD_SMEM, (cudaStream_t)stream, map_qkv, map_do, (const bf16*)out, (const bf16*)dout,
                                                                            lse, (bf16*)dqkv, B, T, H, scale);

@@ -58,7 +58,7 @@ def main(B=128):
             raise SystemExit(lib.dfu_last_error().decode())
     ev[1].record()
     torch.cuda.synchronize()
-    print("attn_fwd B=%d: %.1f us per launch (5 back-to-back launches, tracing build)" % (B, ev[0].elapsed_time(ev[1]) * 200))
+    print("attn_fwd B=%d: %.1f us per launch (5 back-to-back launches)" % (B, ev[0].elapsed_time(ev[1]) * 200))
     dout = torch.randn(B * T, H * 64, device="cuda").to(torch.bfloat16)
     dqkv = torch.empty_like(qkv)
     lib.dfu_attention_bwd.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_float, ctypes.c_void_p]
@@ -70,7 +70,9 @@ def main(B=128):
             raise SystemExit(lib.dfu_last_error().decode())
     ev[1].record()
     torch.cuda.synchronize()
-    print("attn_bwd B=%d: %.1f us per launch (5 back-to-back launches, tracing build)" % (B, ev[0].elapsed_time(ev[1]) * 200))
+    print("attn_bwd B=%d: %.1f us per launch (5 back-to-back launches)" % (B, ev[0].elapsed_time(ev[1]) * 200))
+    if not hasattr(lib, "dfu_attn_trace_read_host"):      # DFU_TRACE_LIB = the product library: timings only (e.g. under ncu)
+        return
     buf = (ctypes.c_longlong * (4 * 16 * 12))()
     assert lib.dfu_attn_trace_read_host(buf) == 0
     cats = ["ops_full + D", "wait sd_full", "tmem ld + exp + dS", "wait tile_free", "write P^T/dS^T + arrive", "wait acc_full",
