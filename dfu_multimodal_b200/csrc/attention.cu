@@ -12,8 +12,12 @@
 //   dV += P^T dO, dK += dS^T Q   (A = the smem tiles, K-major)      dQ += dS K   (A = the same dS^T tile, MN-major)
 // in 2 x 2 (key tile, query chunk) steps of 128 x 128, all five accumulators in the 512 TMEM columns.
 //
-// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 softmax /
-// epilogue (warp w owns TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter split the columns).
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (the whole warp walks the schedule, one elected lane
+// issues), warp 2 TMEM allocator, warps 4-19 softmax / epilogue (warp w owns TMEM lanes 32*(w%4)..+31; the four warps of a
+// lane quarter split the columns).  Everything that leaves the chip in rows -- O, dQ, dK, dV -- is staged in a shared-memory
+// tile that is free at that moment and stored by TMA through a 3-D view that clips the rows >= T: a thread owns one row, so
+// direct stores touch 32 different 128-byte lines per instruction.  How the time of a head splits over the phases of
+// each kernel is measured by tools/gpu_attn_trace.py (a second build with -DDFU_ATTN_TRACE); DESIGN.md 5.2 has the numbers.
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "../../include/dfu_b200.h"

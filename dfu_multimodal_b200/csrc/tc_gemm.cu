@@ -94,6 +94,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp, the same one every time (see tc_common.cuh)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     asm volatile(
@@ -429,8 +441,11 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             // ------------------------------------------------------------------ MMA issuer (leader CTA only when CG == 2)
+            // The whole warp walks the schedule and waits; one elected lane issues.  (Under a `lane == 0` branch ptxas wraps
+            // every tcgen05.mma in a vote / elect loop with R2UR moves, ~17 instructions per MMA -- more than a 128 x 64 x 16
+            // MMA takes on the narrow tiles of the ResNet branch; measured on the attention kernels)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) |
                                    ((uint32_t)p.b_mn << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
@@ -451,21 +466,25 @@ dfu_tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
                     const uint32_t sb = sa + A_TILE_BYTES;
+                    if (elect_one()) {
+                        const uint64_t adesc0 = p.a_mn ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
+                        const uint64_t bdesc0 = p.b_mn ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+                        const uint64_t astep = p.a_mn ? (2048 >> 4) : (32 >> 4), bstep = p.b_mn ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        const uint64_t adesc = p.a_mn ? make_desc(sa + k * 2048, 8192, 1024)
-                                                      : make_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bdesc = p.b_mn ? make_desc(sb + k * 2048, 8192, 1024)
-                                                      : make_desc(sb + k * 32, 16, 1024);
-                        if (CG == 2) tc_mma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            if (CG == 2) tc_mma_f16_2sm(tmem_d, adesc0 + k * astep, bdesc0 + k * bstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else tc_mma_f16(tmem_d, adesc0 + k * astep, bdesc0 + k * bstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+                        if (CG == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+                        // accumulator complete -> epilogue warps (of both CTAs)
+                        if (kb + 1 == kb1) {
+                            if (CG == 2) tc_commit_2sm(&tmem_full_bar[acc]); else tc_commit(&tmem_full_bar[acc]);
+                        }
                     }
-                    // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-                    if (CG == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                // accumulator complete -> epilogue warps (of both CTAs)
-                if (CG == 2) tc_commit_2sm(&tmem_full_bar[acc]); else tc_commit(&tmem_full_bar[acc]);
             }
         }
     } else if (warp_idx >= EPI_WARP0) {
