@@ -213,7 +213,8 @@ int dfu_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, 
  * F.scaled_dot_product_attention / the bmm-softmax-bmm chain).  head_dim is 64, 128 < T <= 208 tokens.
  *   qkv  [B*T, 3*H*64] bf16, timm order [3][H][64] along the row;  out [B*T, H*64] bf16;
  *   lse  [B, H, T] fp32 = log sum_j exp(scale * q.k_j)  (saved for the backward pass instead of the [T,T] matrix).
- * tcgen05 MMAs with S/O (forward) and S^T/dP^T/dV/dK/dQ (backward) accumulators in TMEM; P never leaves the SM. */
+ * tcgen05 MMAs with S/O (forward) and S^T/dP^T/dV/dK/dQ (backward) accumulators in TMEM; P never leaves the SM.
+ * Every buffer 16-byte aligned (they are read and written through TMA tensor maps). */
 int dfu_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t T, int32_t H, float scale, void* stream);
 /* dqkv [B*T, 3*H*64] bf16 (every element written). */
 int dfu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t B,
