@@ -86,3 +86,15 @@ def test_augment_params_struct_matches_header_layout():
     names = [re.sub(r"\[.*", "", d.strip().split()[-1]) for d in body.split(";") if d.strip()]
     assert names == [f[0] for f in _lib.AugmentParams._fields_]
     assert ctypes.sizeof(_lib.AugmentParams) == 4 * (2 + 6 + 1 + 6 + 1 + 3 + 3) + 2 * 224 * 2
+
+
+def test_attention_trace_variant_compiles(tmp_path):
+    """tools/gpu_attn_trace.py builds a second library with -DDFU_ATTN_TRACE (phase clocks of the attention kernels); the
+    instrumented source must keep compiling for sm_100a -- it is otherwise only built when someone profiles."""
+    import subprocess
+    from dfu_multimodal_b200 import build as B
+    flags = [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    obj = str(tmp_path / "attention_trace.o")
+    subprocess.check_call([B._nvcc()] + flags + ["-DDFU_ATTN_TRACE", "-c", os.path.join(B.CSRC, "attention.cu"), "-o", obj])
+    sym = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    assert "dfu_attn_trace_read_host" in sym

@@ -16,11 +16,12 @@ LOGIT_TOL = 2e-2
 # 0.9608 / 0.9788 in three runs of one build; oracle 0.9453).  Measured spread of |mean_cuda - mean_oracle| / mean_oracle
 # over the 200 steps, nine B200 runs across four builds and both attention implementations: 0.17, 0.55, 0.56, 0.90, 0.94,
 # 1.24, 1.39, 2.95 % (tools/gpu_learning_curve_spread.py, profiles/r02v_learning_curve_spread.txt); first-window means
-# 0.6429 .. 0.6624 against the oracle's 0.6486.  The bounds below are that spread with margin; the deterministic checks are
+# 0.6429 .. 0.6624 against the oracle's 0.6486, second-window means (the loss falls through 0.15 -> 0.02 there) 0.0631 .. 0.0725
+# against 0.0674.  The bounds below are that spread with margin (window: 3 % + 1e-2); the deterministic checks are
 # step 0 (1 %), the stable-regime curve (test_loss_curve_200_steps_against_golden, the north-star's 1 %) and the
 # kernel-level gradient tests.  A path with a broken backward or optimizer stays at ln 2 and misses every window by 10x.
 LEARNING_WINDOW_REL = 0.03
-LEARNING_WINDOW_ABS = 5e-3
+LEARNING_WINDOW_ABS = 1e-2
 LEARNING_MEAN_REL = 0.05
 
 
@@ -317,7 +318,7 @@ def test_learning_loss_curve_200_steps_against_golden(R, D, dev, golden_dir):
     oracle/make_loss_curve.py).  The oracle memorises the set: ln 2 -> below 0.1 after ~26 steps -> below 1e-3.  A path
     with a broken backward or optimizer stays at ln 2 and fails every bound below.
     Bounds: step 0 (identical weights) within 1 %; the mean over the 200 steps within 5 % and every 25-step window mean
-    within 3 % + 5e-3 of the oracle's -- the measured run-to-run spread of this transient with margin, see the comment at
+    within 3 % + 1e-2 of the oracle's -- the measured run-to-run spread of this transient with margin, see the comment at
     LEARNING_MEAN_REL (measured: up to 2.1 % in the first window, 5e-3 absolute while the loss falls through 0.15 -> 0.02 in
     the second -- the runs memorise at slightly different steps --, < 1e-3 later)."""
     import json
